@@ -1,0 +1,65 @@
+// Host-side loader: ARPA text -> the open-addressing tables of lm_tables.h.
+// Plain C++ (no CUDA) so that the library and the tests' host simulation share it.
+//
+// On-disk format accepted: the ARPA files lmplz writes, including the shape CoRal's
+// patch produces (R:src/coral/ngram.py:147-169: "ngram 1=" bumped by one and a second
+// "</s>" unigram line copied from "<s>"); a duplicate unigram keeps its first slot.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "lm_tables.h"
+
+namespace coral {
+
+struct HostLm {
+  std::string path;
+  int order = 0;
+  std::vector<uint64_t> counts;  // declared "ngram n=" values
+  std::vector<uint64_t> loaded;  // n-grams actually stored per order
+  std::vector<std::string> words;  // id -> utf-8
+  std::unordered_map<std::string, uint32_t> vocab;
+  std::vector<UniEntry> uni;
+  std::vector<NgSlot> ng;
+  uint64_t ng_mask = 0;
+  uint32_t bos_id = 0, eos_id = 0;
+};
+
+struct HostLexicon {
+  std::vector<LexSlot> lex;
+  uint64_t lex_mask = 0;
+  int has_unigrams = 0;
+  uint64_t n_entries = 0;
+};
+
+// returns 0 on success; negative status + message otherwise
+int load_arpa(const char* path, HostLm& lm, std::string& err);
+
+// unigrams == nullptr <=> pyctcdecode's ``unigrams=None`` (no unigram set, no char trie)
+int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams, HostLexicon& out,
+                  std::string& err);
+
+bool utf8_to_u32(const std::string& s, std::u32string& out);
+uint64_t hash_word(const std::u32string& w);
+
+inline LmView make_view(const HostLm& lm, const HostLexicon& lx, const UniEntry* uni,
+                        const NgSlot* ng, const LexSlot* lex) {
+  LmView v;
+  v.uni = uni;
+  v.ng = ng;
+  v.lex = lex;
+  v.ng_mask = lm.ng_mask;
+  v.lex_mask = lx.lex_mask;
+  v.n_vocab = (uint32_t)lm.uni.size();
+  v.order = lm.order;
+  v.bos_id = lm.bos_id;
+  v.eos_id = lm.eos_id;
+  v.has_unigrams = lx.has_unigrams;
+  v.present = 1;
+  return v;
+}
+
+}  // namespace coral
