@@ -1,0 +1,404 @@
+// C-ABI: decoder handle and the batched prefix-beam-search launch.
+// The per-utterance algorithm lives in beam_core.h; this file owns the persistent
+// kernel (one thread group per utterance at a time, work-stealing over the batch),
+// the HBM scratch arenas and pyctcdecode's probabilities-vs-logits detection.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "handles.h"
+
+namespace coral {
+
+struct BeamLaunch {
+  DecodeParams P;
+  LmView lm;
+  const float* logits;
+  const int32_t* lengths;
+  const int32_t* order;
+  const int32_t* is_prob;
+  int32_t B;
+  int32_t* out_n;
+  double* out_logit;
+  double* out_comb;
+  uint8_t* out_tokens;
+  int32_t* out_len;
+  int32_t* out_status;
+  unsigned long long* stats;
+  uint8_t* scratch;
+  unsigned long long slot_bytes;
+  uint32_t node_cap, bnd_cap, ch_size, outs_cap;
+  uint32_t* slot_epoch;
+  int32_t* work;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_cap, uint32_t ch_size,
+                                              uint32_t outs_cap, size_t off[7]) {
+  size_t o = 0;
+  off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
+  off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
+  off[2] = o; o = align16(o + (size_t)ch_size * 8);        // ch_keys
+  off[3] = o; o = align16(o + (size_t)ch_size * 4);        // ch_vals
+  off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
+  off[5] = o; o = align16(o + (size_t)outs_cap * sizeof(OutRec));
+  off[6] = o; o = align16(o + (size_t)outs_cap * 2);       // surv
+  return o;
+}
+
+// One thread group (= one CTA of NT threads) decodes one utterance at a time and then
+// fetches the next from a global counter; `order` lets the host hand out long
+// utterances first so the tail of the batch is short.
+template <int NT, int BW, int OUTC>
+__global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Dec = BeamDecoder<NT, BW, OUTC>;
+  typename Dec::Sm& sm = *reinterpret_cast<typename Dec::Sm*>(smem_raw);
+  const uint32_t slot = blockIdx.x;
+  SlotScratch sc;
+  {
+    size_t off[7];
+    slot_layout(L.node_cap, L.bnd_cap, L.ch_size, L.outs_cap, off);
+    uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
+    sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
+    sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
+    sc.ch_keys = reinterpret_cast<unsigned long long*>(base + off[2]);
+    sc.ch_vals = reinterpret_cast<uint32_t*>(base + off[3]);
+    sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
+    sc.outs_g = reinterpret_cast<OutRec*>(base + off[5]);
+    sc.surv_g = reinterpret_cast<uint16_t*>(base + off[6]);
+    sc.node_cap = L.node_cap;
+    sc.bnd_cap = L.bnd_cap;
+    sc.ch_mask = L.ch_size - 1;
+    sc.outs_cap = L.outs_cap;
+  }
+  uint32_t epoch = L.slot_epoch[slot];
+  for (;;) {
+    if (threadIdx.x == 0) sm.utt = atomicAdd(L.work, 1);
+    group_sync<NT>();
+    const int i = sm.utt;
+    if (i >= L.B) break;
+    const int u = L.order ? L.order[i] : i;
+    sc.epoch = ++epoch;
+    UttIO io;
+    io.logits = L.logits + (size_t)u * L.P.T_max * L.P.V;
+    io.T = L.lengths[u];
+    io.is_prob = L.is_prob ? L.is_prob[u] : 0;
+    io.out_n = L.out_n + u;
+    io.out_logit = L.out_logit + (size_t)u * L.P.n_best;
+    io.out_comb = L.out_comb + (size_t)u * L.P.n_best;
+    io.out_tokens = L.out_tokens + (size_t)u * L.P.n_best * L.P.T_max;
+    io.out_len = L.out_len + (size_t)u * L.P.n_best;
+    io.out_status = L.out_status + u;
+    io.stats = L.stats;
+    Dec::decode(sm, L.lm, L.P, sc, io);
+    group_sync<NT>();
+  }
+  if (threadIdx.x == 0) L.slot_epoch[slot] = epoch;
+}
+
+// ---- pyctcdecode's input check: math.isclose(logits.sum(axis=1).mean(), 1) -------------
+// (SURVEY A5 step 2). Both reductions are float32 in numpy's pairwise order so that the
+// float32 mean -- which passes the test only when it is exactly 1.0f -- is reproduced.
+__device__ float pw_leaf(const float* a, int n) {
+  if (n < 8) {
+    float r = 0.0f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  float r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+  float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                      __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) s = __fadd_rn(s, a[i]);
+  return s;
+}
+__device__ float pw_sum(const float* a, int n) {
+  if (n <= 128) return pw_leaf(a, n);
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(pw_sum(a, n2), pw_sum(a + n2, n - n2));
+}
+
+__global__ void classify_input_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lengths,
+                                      int B, int T_max, int V, float* __restrict__ rowsum,
+                                      int32_t* __restrict__ is_prob) {
+  const int u = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32);
+  const int lane = threadIdx.x % 32;
+  if (u >= B) return;
+  const int T = lengths[u];
+  float* rs = rowsum + (size_t)u * T_max;
+  for (int t = lane; t < T; t += 32) {
+    const float* row = logits + ((size_t)u * T_max + t) * V;
+    rs[t] = V <= 128 ? pw_leaf(row, V) : pw_sum(row, V);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int p = 0;
+    if (T > 0) {
+      const float mean = __fdiv_rn(pw_sum(rs, T), (float)T);
+      p = mean == 1.0f ? 1 : 0;
+    }
+    is_prob[u] = p;
+  }
+}
+
+template <int NT, int BW, int OUTC>
+static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStream_t st) {
+  using Dec = BeamDecoder<NT, BW, OUTC>;
+  const size_t smem = sizeof(typename Dec::Sm);
+  auto kern = beam_search_kernel<NT, BW, OUTC>;
+  CORAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) return fail(CORAL_ECUDA, "beam kernel does not fit on an SM");
+  const uint32_t want = (uint32_t)std::min<int64_t>((int64_t)B, (int64_t)per_sm * sm_count(dec->device));
+
+  // scratch: worst-case arenas per slot (every frame can add beam_width letter nodes and
+  // beam_width word-boundary nodes), bounded by a memory budget.
+  const uint64_t T = (uint64_t)std::max(1, L.P.T_max);
+  const uint64_t bw = (uint64_t)L.P.beam_width;
+  uint32_t node_cap = (uint32_t)std::min<uint64_t>(2 * bw * T + 64, (1u << 24) - 1);
+  uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
+  uint32_t ch_size = 64;
+  while (ch_size < 2 * node_cap) ch_size <<= 1;
+  uint32_t outs_cap = (uint32_t)(bw * (uint64_t)(L.P.V + 1) + 64);
+  size_t off[7];
+  const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
+  size_t free_b = 0, total_b = 0;
+  CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + dec->scratch_bytes) / 2);
+  uint32_t n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(want, budget / slot_bytes));
+  const bool fits = dec->d_scratch && dec->node_cap >= node_cap && dec->bnd_cap >= bnd_cap &&
+                    dec->ch_size >= ch_size && dec->outs_cap >= outs_cap && dec->n_slots >= n_slots;
+  if (fits) {
+    // reuse the arena with the (larger) capacities it was laid out for
+    node_cap = dec->node_cap;
+    bnd_cap = dec->bnd_cap;
+    ch_size = dec->ch_size;
+    outs_cap = dec->outs_cap;
+  } else {
+    node_cap = std::max(node_cap, dec->node_cap);
+    bnd_cap = std::max(bnd_cap, dec->bnd_cap);
+    ch_size = std::max(ch_size, dec->ch_size);
+    outs_cap = std::max(outs_cap, dec->outs_cap);
+    const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
+    n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max(want, dec->n_slots), budget / sb));
+    // wait for earlier launches that may still use the old arena, then rebuild it
+    CORAL_CUDA_OK(cudaDeviceSynchronize());
+    if (dec->d_scratch) cudaFree(dec->d_scratch);
+    if (dec->d_slot_epoch) cudaFree(dec->d_slot_epoch);
+    dec->d_scratch = nullptr;
+    dec->d_slot_epoch = nullptr;
+    dec->scratch_bytes = 0;
+    dec->n_slots = 0;
+    const size_t bytes = sb * n_slots;
+    CORAL_CUDA_OK(cudaMalloc(&dec->d_scratch, bytes));
+    CORAL_CUDA_OK(cudaMalloc(&dec->d_slot_epoch, sizeof(uint32_t) * n_slots));
+    CORAL_CUDA_OK(cudaMemsetAsync(dec->d_slot_epoch, 0, sizeof(uint32_t) * n_slots, st));
+    // child-table keys must start at 0 (= "never used"); everything else is written before read
+    for (uint32_t s = 0; s < n_slots; ++s)
+      CORAL_CUDA_OK(cudaMemsetAsync(dec->d_scratch + (size_t)s * sb + off[2], 0, (size_t)ch_size * 8, st));
+    dec->scratch_bytes = bytes;
+    dec->slot_bytes = sb;
+    dec->n_slots = n_slots;
+    dec->node_cap = node_cap;
+    dec->bnd_cap = bnd_cap;
+    dec->ch_size = ch_size;
+    dec->outs_cap = outs_cap;
+  }
+  if (!dec->d_work) CORAL_CUDA_OK(cudaMalloc(&dec->d_work, sizeof(int32_t)));
+  CORAL_CUDA_OK(cudaMemsetAsync(dec->d_work, 0, sizeof(int32_t), st));
+  L.scratch = dec->d_scratch;
+  L.slot_bytes = dec->slot_bytes;
+  L.node_cap = node_cap;
+  L.bnd_cap = bnd_cap;
+  L.ch_size = ch_size;
+  L.outs_cap = outs_cap;
+  L.slot_epoch = dec->d_slot_epoch;
+  L.work = dec->d_work;
+  const uint32_t grid = std::min<uint32_t>(dec->n_slots, std::max<uint32_t>(1, want));
+  kern<<<grid, NT, smem, st>>>(L);
+  CORAL_CUDA_OK(cudaGetLastError());
+  return CORAL_OK;
+}
+
+}  // namespace coral
+
+using namespace coral;
+
+extern "C" {
+
+int32_t coral_decoder_create(const uint32_t* label_cps, const int32_t* label_offsets, int32_t n_labels,
+                             int32_t blank_id, int32_t space_id, const coral_lm* lm, const uint32_t* unigram_cps,
+                             const int64_t* unigram_offsets, int64_t n_unigrams, int32_t device,
+                             coral_decoder** out) {
+  if (!out || !label_offsets || (!label_cps && n_labels > 0)) return fail(CORAL_EARG, "coral_decoder_create: null argument");
+  *out = nullptr;
+  if (n_labels < 1 || n_labels > kVMax)
+    return fail(CORAL_EARG, "alphabet size must be in [1, 64] in this build");
+  if (blank_id < 0 || blank_id >= n_labels) return fail(CORAL_EARG, "blank_id outside the alphabet");
+  if (space_id >= n_labels) return fail(CORAL_EARG, "space_id outside the alphabet");
+  if (lm && lm->device != device) return fail(CORAL_EARG, "LM and decoder must live on the same device");
+  coral_decoder* d = new coral_decoder();
+  memset(&d->P, 0, sizeof(d->P));
+  d->lm = lm;
+  d->device = device;
+  d->P.V = n_labels;
+  d->P.blank_id = blank_id;
+  d->P.space_id = space_id;
+  d->P.alpha = 0.5;
+  d->P.beta = 1.5;
+  d->P.unk_score_offset = -10.0;
+  d->P.score_boundary = 1;
+  d->P.log_base_change = 2.302585092994046;  // 1.0 / np.log10(np.e), UP:pyctcdecode constants.py
+  for (int v = 0; v < n_labels; ++v) {
+    const int n = label_offsets[v + 1] - label_offsets[v];
+    if (n < 0 || n > kMaxLabelCps) { delete d; return fail(CORAL_EARG, "alphabet label longer than 8 code points"); }
+    if ((n == 0) != (v == blank_id)) { delete d; return fail(CORAL_EARG, "exactly the blank label must be empty"); }
+    d->P.label_ncp[v] = (uint8_t)n;
+    for (int q = 0; q < n; ++q) d->P.label_cps[v][q] = label_cps[label_offsets[v] + q];
+  }
+  if (lm) {
+    std::vector<std::u32string> uni;
+    if (n_unigrams >= 0) {
+      uni.reserve((size_t)n_unigrams);
+      for (int64_t i = 0; i < n_unigrams; ++i)
+        uni.emplace_back(reinterpret_cast<const char32_t*>(unigram_cps + unigram_offsets[i]),
+                         (size_t)(unigram_offsets[i + 1] - unigram_offsets[i]));
+    }
+    std::string err;
+    const int rc = build_lexicon(lm->host, n_unigrams >= 0 ? &uni : nullptr, d->lex, err);
+    if (rc != 0) { delete d; return fail(rc, err); }
+    DeviceGuard g(device);
+    const size_t lb = d->lex.lex.size() * sizeof(LexSlot);
+    cudaError_t e;
+    if ((e = cudaMalloc(&d->d_lex, lb)) != cudaSuccess ||
+        (e = cudaMemcpy(d->d_lex, d->lex.lex.data(), lb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      std::string m = std::string("uploading lexicon: ") + cudaGetErrorString(e);
+      coral_decoder_free(d);
+      return fail(CORAL_ECUDA, m);
+    }
+    d->device_bytes = lb;
+  }
+  *out = d;
+  return CORAL_OK;
+}
+
+int32_t coral_decoder_free(coral_decoder* d) {
+  if (!d) return CORAL_OK;
+  DeviceGuard g(d->device);
+  cudaDeviceSynchronize();
+  if (d->d_lex) cudaFree(d->d_lex);
+  if (d->d_scratch) cudaFree(d->d_scratch);
+  if (d->d_slot_epoch) cudaFree(d->d_slot_epoch);
+  if (d->d_work) cudaFree(d->d_work);
+  if (d->d_rowsum) cudaFree(d->d_rowsum);
+  if (d->d_is_prob) cudaFree(d->d_is_prob);
+  delete d;
+  return CORAL_OK;
+}
+
+int32_t coral_decoder_set_params(coral_decoder* d, double alpha, double beta, double unk_score_offset,
+                                 int32_t score_boundary) {
+  if (!d) return fail(CORAL_EARG, "coral_decoder_set_params: null handle");
+  d->P.alpha = alpha;
+  d->P.beta = beta;
+  d->P.unk_score_offset = unk_score_offset;
+  d->P.score_boundary = score_boundary ? 1 : 0;
+  return CORAL_OK;
+}
+
+int32_t coral_decoder_info(const coral_decoder* d, uint64_t* lexicon_entries, uint64_t* device_bytes) {
+  if (!d) return fail(CORAL_EARG, "coral_decoder_info: null handle");
+  if (lexicon_entries) *lexicon_entries = d->lex.n_entries;
+  if (device_bytes) *device_bytes = d->device_bytes + d->scratch_bytes;
+  return CORAL_OK;
+}
+
+int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
+                              const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V, int32_t beam_width,
+                              double beam_prune_logp, double token_min_logp, int32_t prune_history,
+                              int32_t input_mode, int32_t n_best, int32_t* out_n_beams_dev,
+                              double* out_logit_score_dev, double* out_lm_score_dev, uint8_t* out_tokens_dev,
+                              int32_t* out_lens_dev, int32_t* out_status_dev, uint64_t* stats_dev, void* stream) {
+  if (!dec) return fail(CORAL_EARG, "coral_ctc_beam_decode: null decoder");
+  if (B < 0 || T_max < 0) return fail(CORAL_EARG, "negative batch or frame count");
+  if (V != dec->P.V)
+    return fail(CORAL_EARG, "Input logits have vocabulary size " + std::to_string(V) + ", but the alphabet is size " +
+                                std::to_string(dec->P.V) + ". Need logits of shape: (time, vocabulary)");
+  if (beam_width < 1 || beam_width > 512) return fail(CORAL_EARG, "beam_width must be in [1, 512]");
+  if (n_best < 1 || n_best > beam_width) return fail(CORAL_EARG, "n_best must be in [1, beam_width]");
+  if (prune_history) return fail(CORAL_EARG, "prune_history=True is not implemented (SURVEY 8f N4)");
+  if (input_mode < 0 || input_mode > 2) return fail(CORAL_EARG, "input_mode must be 0, 1 or 2");
+  if (B == 0) return CORAL_OK;
+  if (!logits_dev || !lengths_dev || !out_n_beams_dev || !out_logit_score_dev || !out_lm_score_dev ||
+      !out_tokens_dev || !out_lens_dev || !out_status_dev)
+    return fail(CORAL_EARG, "coral_ctc_beam_decode: null buffer");
+  DeviceGuard g(dec->device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  BeamLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.P = dec->P;
+  L.P.beam_width = beam_width;
+  L.P.n_best = n_best;
+  L.P.T_max = T_max > 0 ? T_max : 1;
+  L.P.input_mode = input_mode;
+  L.P.token_min_logp = (float)token_min_logp;
+  L.P.beam_prune_logp = beam_prune_logp;
+  if (dec->lm) {
+    L.lm = make_view(dec->lm->host, dec->lex, dec->lm->d_uni, dec->lm->d_ng, dec->d_lex);
+  } else {
+    L.lm.present = 0;
+  }
+  L.logits = logits_dev;
+  L.lengths = lengths_dev;
+  L.order = order_dev;
+  L.B = B;
+  L.out_n = out_n_beams_dev;
+  L.out_logit = out_logit_score_dev;
+  L.out_comb = out_lm_score_dev;
+  L.out_tokens = out_tokens_dev;
+  L.out_len = out_lens_dev;
+  L.out_status = out_status_dev;
+  L.stats = reinterpret_cast<unsigned long long*>(stats_dev);
+
+  if (input_mode == 0) {
+    const size_t need = (size_t)B * L.P.T_max;
+    if (dec->rowsum_elems < need) {
+      CORAL_CUDA_OK(cudaDeviceSynchronize());
+      if (dec->d_rowsum) cudaFree(dec->d_rowsum);
+      dec->d_rowsum = nullptr;
+      CORAL_CUDA_OK(cudaMalloc(&dec->d_rowsum, need * sizeof(float)));
+      dec->rowsum_elems = need;
+    }
+    if (dec->is_prob_elems < (size_t)B) {
+      CORAL_CUDA_OK(cudaDeviceSynchronize());
+      if (dec->d_is_prob) cudaFree(dec->d_is_prob);
+      dec->d_is_prob = nullptr;
+      CORAL_CUDA_OK(cudaMalloc(&dec->d_is_prob, (size_t)B * sizeof(int32_t)));
+      dec->is_prob_elems = (size_t)B;
+    }
+    const int threads = 128;
+    const unsigned blocks = (unsigned)(((size_t)B * 32 + threads - 1) / threads);
+    classify_input_kernel<<<blocks, threads, 0, st>>>(logits_dev, lengths_dev, B, L.P.T_max, V, dec->d_rowsum,
+                                                      dec->d_is_prob);
+    CORAL_CUDA_OK(cudaGetLastError());
+    L.is_prob = dec->d_is_prob;
+  }
+
+  if (beam_width <= 32) return launch_beam<32, 32, 128>(dec, L, B, st);
+  if (beam_width <= 64) return launch_beam<32, 64, 192>(dec, L, B, st);
+  if (beam_width <= 128) return launch_beam<32, 128, 320>(dec, L, B, st);
+  if (beam_width <= 256) return launch_beam<64, 256, 640>(dec, L, B, st);
+  return launch_beam<128, 512, 1280>(dec, L, B, st);
+}
+
+}  // extern "C"

@@ -59,8 +59,7 @@ __device__ __forceinline__ void group_sync() {
   if (NT == 32) {
     __syncwarp();
   } else {
-    const unsigned id = 1u + threadIdx.x / NT;
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NT) : "memory");
+    __syncthreads();  // one thread group per CTA
   }
 }
 #define CORAL_LANES(NT) for (int lane = (int)(threadIdx.x % (NT)), _once = 1; _once; _once = 0)
@@ -231,7 +230,7 @@ CORAL_HD double partial_score(const DecodeParams& P, uint32_t wlen, uint32_t fla
 }
 
 // pyctcdecode LanguageModel.score: alpha * log10-score * ln10 + beta
-CORAL_HD double lm_word_score(const LmView& lm, const DecodeParams& P, const LmState& in, uint32_t wid,
+CORAL_DEV double lm_word_score(const LmView& lm, const DecodeParams& P, const LmState& in, uint32_t wid,
                               bool oov, bool is_last, LmState& out, unsigned long long* stats) {
   int np = 0;
   double x = (double)lm_base_score(lm, in, wid, out, &np);

@@ -1,0 +1,36 @@
+// Opaque handle definitions shared by the C-ABI translation units.
+#pragma once
+#include <stdint.h>
+
+#include "beam_core.h"
+#include "lm_host.h"
+
+struct coral_lm {
+  coral::HostLm host;
+  coral::HostLexicon vocab_lex;  // LM vocabulary only (used by the LM debug entry points)
+  coral::UniEntry* d_uni = nullptr;
+  coral::NgSlot* d_ng = nullptr;
+  coral::LexSlot* d_lex = nullptr;
+  int device = 0;
+  uint64_t device_bytes = 0;
+};
+
+struct coral_decoder {
+  const coral_lm* lm = nullptr;
+  coral::HostLexicon lex;  // LM vocabulary U unigram list, with pyctcdecode's flags
+  coral::LexSlot* d_lex = nullptr;
+  coral::DecodeParams P;   // alphabet + current alpha/beta/unk/boundary
+  int device = 0;
+  // scratch arenas in HBM, grown lazily, reused call after call
+  uint8_t* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  size_t slot_bytes = 0;
+  uint32_t n_slots = 0;
+  uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0;
+  uint32_t* d_slot_epoch = nullptr;
+  int32_t* d_work = nullptr;
+  float* d_rowsum = nullptr;   // [B * T_max] for the probabilities-vs-logits detection
+  int32_t* d_is_prob = nullptr;
+  size_t rowsum_elems = 0, is_prob_elems = 0;
+  uint64_t device_bytes = 0;
+};

@@ -1,0 +1,370 @@
+"""``BeamSearchDecoderCTC`` / ``build_ctcdecoder``: pyctcdecode's surface over the CUDA decoder.
+
+Host-side mirror of UP:pyctcdecode 0.5.0 ``decoder.py``: same
+names, argument meaning, defaults, return tuples and error behaviour, so that
+``Wav2Vec2ProcessorWithLM`` (HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:
+80-84, :143, :160-206, :365-367, :398-406, :565-572), the HF ASR pipeline
+(HF:pipelines/automatic_speech_recognition.py:612-623) and CoRal
+(R:src/coral/ngram.py:341-348) can use it unchanged. All decoding runs in
+``coral_ctc_beam_decode`` on the GPU, a whole batch per launch; the ``pool`` argument is
+accepted and ignored (no process pool is needed).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+
+import numpy as np
+
+from . import _lib
+from .alphabet import (
+    DEFAULT_ALPHA,
+    DEFAULT_BEAM_WIDTH,
+    DEFAULT_BETA,
+    DEFAULT_HOTWORD_WEIGHT,
+    DEFAULT_MIN_TOKEN_LOGP,
+    DEFAULT_PRUNE_BEAMS,
+    DEFAULT_PRUNE_LOGP,
+    DEFAULT_SCORE_LM_BOUNDARY,
+    DEFAULT_UNK_LOGP_OFFSET,
+    Alphabet,
+)
+from .language_model import KenlmModel, LanguageModel, load_unigram_set_from_arpa
+from .textio import encode_utf32
+
+logger = logging.getLogger(__name__)
+
+MAX_BEAM_WIDTH = 512
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("coral_b200 needs a CUDA device: there is no CPU path")
+    return torch
+
+
+class DecodedBatch:
+    """Raw result of one batched launch (host numpy arrays)."""
+
+    def __init__(self, n_beams, logit, comb, tokens, lens, status, stats=None):
+        self.n_beams = n_beams
+        self.logit_score = logit
+        self.lm_score = comb
+        self.tokens = tokens
+        self.lens = lens
+        self.status = status
+        self.stats = stats
+
+
+class BeamSearchDecoderCTC:
+    # pyctcdecode keeps language models in a class-level container keyed by a random id
+    # so that fork pools share them; HF reads and writes attributes through it.
+    model_container: dict[bytes, LanguageModel | None] = {}
+
+    _ALPHABET_SERIALIZED_FILENAME = "alphabet.json"
+    _LANGUAGE_MODEL_SERIALIZED_DIRECTORY = "language_model"
+
+    def __init__(self, alphabet: Alphabet, language_model: LanguageModel | None = None,
+                 device: int | None = None) -> None:
+        self._alphabet = alphabet
+        self._idx2vocab = {n: c for n, c in enumerate(self._alphabet.labels)}
+        self._is_bpe = alphabet.is_bpe
+        self._model_key = os.urandom(16)
+        BeamSearchDecoderCTC.model_container[self._model_key] = language_model
+        self._device = device
+        self._h = None
+        labels = self._alphabet.labels
+        if len(labels) > 64:
+            raise NotImplementedError("alphabets above 64 entries are not supported by this build")
+        self._blank_id = labels.index("")
+        self._space_id = labels.index(" ") if " " in labels else -1
+        # id -> code point table for the fast token->string path (single-code-point labels)
+        self._single_cp = all(len(c) <= 1 for c in labels)
+        self._cp_table = np.array([ord(c) if len(c) == 1 else 0 for c in labels], dtype=np.uint32)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def _language_model(self) -> LanguageModel | None:
+        return BeamSearchDecoderCTC.model_container[self._model_key]
+
+    def cleanup(self) -> None:
+        BeamSearchDecoderCTC.model_container.pop(self._model_key, None)
+
+    def reset_params(self, alpha=None, beta=None, unk_score_offset=None, lm_score_boundary=None) -> None:
+        language_model = self._language_model
+        if language_model is None:
+            return
+        if alpha is not None:
+            language_model.alpha = alpha
+        if beta is not None:
+            language_model.beta = beta
+        if unk_score_offset is not None:
+            language_model.unk_score_offset = unk_score_offset
+        if lm_score_boundary is not None:
+            language_model.score_boundary = lm_score_boundary
+
+    def _handle(self):
+        if self._h is None:
+            torch = _torch()
+            lm = self._language_model
+            if self._device is None:
+                self._device = lm.kenlm_model.device if lm is not None else torch.cuda.current_device()
+            lib = _lib.load()
+            cps, off = encode_utf32(self._alphabet.labels)
+            off32 = off.astype(np.int32)
+            h = C.c_void_p()
+            if lm is not None and lm.unigrams is not None:
+                ucps, uoff = encode_utf32(lm.unigrams)
+                n_uni = len(lm.unigrams)
+            else:
+                ucps, uoff, n_uni = np.zeros(1, np.uint32), np.zeros(1, np.int64), -1
+            _lib.check(lib.coral_decoder_create(
+                cps.ctypes.data, off32.ctypes.data, len(self._alphabet.labels), self._blank_id, self._space_id,
+                lm.kenlm_model._h if lm is not None else None, ucps.ctypes.data, uoff.ctypes.data, n_uni,
+                self._device, C.byref(h)))
+            self._h = h
+        lm = self._language_model
+        if lm is not None:
+            _lib.check(_lib.load().coral_decoder_set_params(
+                self._h, float(lm.alpha), float(lm.beta), float(lm.unk_score_offset), int(bool(lm.score_boundary))))
+        return self._h
+
+    def __deepcopy__(self, memo):
+        # HF's ProcessorMixin.to_dict() deep-copies its attributes; native handles are shared
+        return self
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().coral_decoder_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _check_logits_dimension(self, logits) -> None:
+        if len(logits.shape) != 2:
+            raise ValueError(
+                "Input logits have %s dimensions, but need 2: (time, vocabulary)" % len(logits.shape)
+            )
+        if logits.shape[-1] != len(self._idx2vocab):
+            raise ValueError(
+                "Input logits shape is %s, but vocabulary is size %s. "
+                "Need logits of shape: (time, vocabulary)" % (logits.shape, len(self._idx2vocab))
+            )
+
+    # --------------------------------------------------------------- batched core
+    def decode_padded(self, logits, lengths, beam_width: int = DEFAULT_BEAM_WIDTH,
+                      beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                      prune_history: bool = False, n_best: int = 1, input_mode: int = 0,
+                      collect_stats: bool = False, to_host: bool = True):
+        """Decode a padded batch ``[B, T_max, V]`` (torch CUDA/CPU tensor or numpy) in one launch.
+
+        ``lengths`` int [B]. Returns :class:`DecodedBatch` (numpy) or, with
+        ``to_host=False``, the tuple of device tensors (the launch stays asynchronous).
+        """
+        torch = _torch()
+        h = self._handle()
+        dev = torch.device("cuda", self._device)
+        if isinstance(logits, np.ndarray):
+            logits = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
+        if logits.dim() != 3:
+            raise ValueError("Input logits have %s dimensions, but need 3: (batch, time, vocabulary)" % logits.dim())
+        if logits.shape[-1] != len(self._idx2vocab):
+            raise ValueError(
+                "Input logits shape is %s, but vocabulary is size %s. "
+                "Need logits of shape: (time, vocabulary)" % (tuple(logits.shape[1:]), len(self._idx2vocab)))
+        if prune_history:
+            raise NotImplementedError("prune_history=True is not implemented yet (SURVEY.md section 8f N4)")
+        if not 1 <= beam_width <= MAX_BEAM_WIDTH:
+            raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
+        n_best = max(1, min(int(n_best), int(beam_width)))
+        d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if isinstance(lengths, np.ndarray):
+            lengths = torch.from_numpy(np.ascontiguousarray(lengths))
+        elif not torch.is_tensor(lengths):
+            lengths = torch.tensor(list(lengths))
+        d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        B, T_max, V = d_logits.shape
+        Tm = max(int(T_max), 1)
+        d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+        d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+        d_logit = torch.zeros((B, n_best), dtype=torch.float64, device=dev)
+        d_comb = torch.zeros((B, n_best), dtype=torch.float64, device=dev)
+        d_tok = torch.zeros((B, n_best, Tm), dtype=torch.uint8, device=dev)
+        d_lens = torch.zeros((B, n_best), dtype=torch.int32, device=dev)
+        d_status = torch.zeros(B, dtype=torch.int32, device=dev)
+        d_stats = torch.zeros(8, dtype=torch.int64, device=dev) if collect_stats else None
+        _lib.check(_lib.load().coral_ctc_beam_decode(
+            h, d_logits.data_ptr(), d_len.data_ptr(), d_order.data_ptr(), B, int(T_max), V, int(beam_width),
+            float(beam_prune_logp), float(token_min_logp), int(bool(prune_history)), int(input_mode), n_best,
+            d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
+            d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None, _lib.stream_ptr(dev)))
+        if not to_host:
+            return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats
+        out = DecodedBatch(d_n.cpu().numpy(), d_logit.cpu().numpy(), d_comb.cpu().numpy(), d_tok.cpu().numpy(),
+                           d_lens.cpu().numpy(), d_status.cpu().numpy(),
+                           d_stats.cpu().numpy() if d_stats is not None else None)
+        if out.status.any():
+            bad = np.nonzero(out.status)[0]
+            raise _lib.CoralError(int(out.status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
+        return out
+
+    def tokens_to_text(self, tokens: np.ndarray, lens: np.ndarray) -> list[str]:
+        """Alphabet indices -> strings for ``[N, T]`` token rows with ``[N]`` lengths."""
+        N, T = tokens.shape
+        lens = lens.astype(np.int64)
+        mask = np.arange(T)[None, :] < lens[:, None]
+        flat = tokens[mask]
+        off = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        if self._single_cp or not np.isin(flat, np.nonzero(self._cp_table == 0)[0]).any():
+            text = self._cp_table[flat].tobytes().decode("utf-32-le")
+            o = off.tolist()
+            return [text[a:b] for a, b in zip(o[:-1], o[1:])]
+        labels = self._alphabet.labels
+        return ["".join(labels[t] for t in flat[off[i] : off[i + 1]]) for i in range(N)]
+
+    def _pad(self, logits_list):
+        """list of [T_i, V] arrays -> (pinned padded [B, T_max, V] tensor, lengths)."""
+        torch = _torch()
+        for lg in logits_list:
+            self._check_logits_dimension(lg)
+        B = len(logits_list)
+        V = len(self._idx2vocab)
+        lengths = np.fromiter((lg.shape[0] for lg in logits_list), dtype=np.int32, count=B)
+        T_max = int(lengths.max()) if B else 0
+        need = B * max(T_max, 1) * V
+        if getattr(self, "_pinned", None) is None or self._pinned.numel() < need:
+            self._pinned = torch.empty(need, dtype=torch.float32, pin_memory=True)
+        buf = self._pinned[:need].view(B, max(T_max, 1), V)
+        nb = buf.numpy()
+        for i, lg in enumerate(logits_list):
+            nb[i, : lengths[i]] = lg
+        return buf, lengths
+
+    # ---------------------------------------------------- pyctcdecode's public API
+    def decode_beams(self, logits, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+                     token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, prune_history: bool = DEFAULT_PRUNE_BEAMS,
+                     hotwords=None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, lm_start_state=None):
+        """All final beams of one utterance: ``[(text, lm_state, [(word, (start, end))],
+        logit_score, lm_score)]``, best first."""
+        return self._decode_beams_many([logits], beam_width, beam_prune_logp, token_min_logp, prune_history,
+                                       hotwords, lm_start_state, n_best=beam_width, mp_safe=False)[0]
+
+    def _decode_beams_many(self, logits_list, beam_width, beam_prune_logp, token_min_logp, prune_history,
+                           hotwords, lm_start_state, n_best, mp_safe):
+        if hotwords:
+            raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
+        if lm_start_state is not None:
+            raise NotImplementedError("lm_start_state (stateful decoding) is not implemented")
+        logits_list = [np.asarray(lg) for lg in logits_list]
+        if not logits_list:
+            return []
+        buf, lengths = self._pad(logits_list)
+        out = self.decode_padded(buf, lengths, beam_width, beam_prune_logp, token_min_logp, prune_history,
+                                 n_best=n_best)
+        B, nb = out.lens.shape
+        texts = self.tokens_to_text(out.tokens.reshape(B * nb, -1), out.lens.reshape(-1))
+        res = []
+        for u in range(B):
+            beams = []
+            for r in range(min(int(out.n_beams[u]), nb)):
+                text = texts[u * nb + r]
+                # word time offsets are not tracked yet: frames are (-1, -1)
+                frames = [(w, (-1, -1)) for w in text.split()]
+                ls, cs = float(out.logit_score[u, r]), float(out.lm_score[u, r])
+                beams.append((text, frames, ls, cs) if mp_safe else (text, None, frames, ls, cs))
+            res.append(beams)
+        return res
+
+    def decode(self, logits, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+               token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, hotwords=None,
+               hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, lm_start_state=None) -> str:
+        return self.decode_batch(None, [logits], beam_width, beam_prune_logp, token_min_logp, hotwords,
+                                 hotword_weight)[0]
+
+    def decode_beams_batch(self, pool, logits_list, beam_width: int = DEFAULT_BEAM_WIDTH,
+                           beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                           prune_history: bool = False, hotwords=None,
+                           hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, n_best: int | None = None):
+        """MP-safe beams (4-tuples: text, frames, logit_score, lm_score) for every utterance.
+        ``pool`` is ignored. ``n_best`` (extension) caps the beams returned per utterance."""
+        return self._decode_beams_many(list(logits_list), beam_width, beam_prune_logp, token_min_logp,
+                                       prune_history, hotwords, None,
+                                       n_best=beam_width if n_best is None else n_best, mp_safe=True)
+
+    def decode_batch(self, pool, logits_list, beam_width: int = DEFAULT_BEAM_WIDTH,
+                     beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                     hotwords=None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, lengths=None) -> list[str]:
+        """Best transcript of every utterance. ``logits_list`` is a list of ``[T_i, V]``
+        arrays, or (extension) a padded ``[B, T_max, V]`` array/tensor with ``lengths``."""
+        if hotwords:
+            raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
+        if lengths is not None:
+            out = self.decode_padded(logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1)
+        else:
+            logits_list = [np.asarray(lg) for lg in logits_list]
+            if not logits_list:
+                return []
+            buf, lens = self._pad(logits_list)
+            out = self.decode_padded(buf, lens, beam_width, beam_prune_logp, token_min_logp, n_best=1)
+        return self.tokens_to_text(out.tokens[:, 0, :], out.lens[:, 0])
+
+    # ------------------------------------------------------------- serialisation
+    def save_to_dir(self, filepath: str) -> None:
+        os.makedirs(filepath, exist_ok=True)
+        with open(os.path.join(filepath, self._ALPHABET_SERIALIZED_FILENAME), "w") as fi:
+            fi.write(self._alphabet.dumps())
+        lm = self._language_model
+        if lm is None:
+            logger.info("decoder has no language model.")
+        else:
+            lm.save_to_dir(os.path.join(filepath, self._LANGUAGE_MODEL_SERIALIZED_DIRECTORY))
+
+    @staticmethod
+    def parse_directory_contents(filepath: str) -> dict:
+        contents = os.listdir(filepath)
+        if BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME not in contents:
+            raise ValueError(f"Could not find alphabet file {BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME}")
+        lm_dir = os.path.join(filepath, BeamSearchDecoderCTC._LANGUAGE_MODEL_SERIALIZED_DIRECTORY)
+        return {
+            "alphabet": os.path.join(filepath, BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME),
+            "language_model": lm_dir if os.path.isdir(lm_dir) else None,
+        }
+
+    @classmethod
+    def load_from_dir(cls, filepath: str, unigram_encoding: str | None = None) -> "BeamSearchDecoderCTC":
+        filenames = cls.parse_directory_contents(filepath)
+        with open(filenames["alphabet"]) as fi:
+            alphabet = Alphabet.loads(fi.read())
+        if filenames["language_model"] is None:
+            language_model = None
+        else:
+            language_model = LanguageModel.load_from_dir(filenames["language_model"], unigram_encoding)
+        return cls(alphabet, language_model=language_model)
+
+    @classmethod
+    def load_from_hf_hub(cls, model_id: str, cache_dir=None, **kwargs) -> "BeamSearchDecoderCTC":
+        from huggingface_hub import snapshot_download
+
+        cached = snapshot_download(model_id, cache_dir=cache_dir, **kwargs)
+        return cls.load_from_dir(cached)
+
+
+def build_ctcdecoder(labels, kenlm_model_path: str | None = None, unigrams=None, alpha: float = DEFAULT_ALPHA,
+                     beta: float = DEFAULT_BETA, unk_score_offset: float = DEFAULT_UNK_LOGP_OFFSET,
+                     lm_score_boundary: bool = DEFAULT_SCORE_LM_BOUNDARY) -> BeamSearchDecoderCTC:
+    """UP:pyctcdecode ``decoder.build_ctcdecoder`` as CoRal calls it at R:src/coral/ngram.py:341-343."""
+    alphabet = Alphabet.build_alphabet(list(labels))
+    if kenlm_model_path is None:
+        return BeamSearchDecoderCTC(alphabet, None)
+    kenlm_model = KenlmModel(kenlm_model_path)
+    if str(kenlm_model_path).endswith(".arpa") and unigrams is None:
+        unigrams = load_unigram_set_from_arpa(kenlm_model_path)
+    language_model = LanguageModel(kenlm_model, unigrams, alpha=alpha, beta=beta,
+                                   unk_score_offset=unk_score_offset, score_boundary=lm_score_boundary)
+    return BeamSearchDecoderCTC(alphabet, language_model)

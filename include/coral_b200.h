@@ -1,0 +1,148 @@
+/* coral_b200 -- C ABI of the B200-native CTC-decode + WER/CER hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every entry
+ * point cites the reference interface it replaces (R: = alexandrainst/coral,
+ * HF: = transformers 5.5.0, UP: = un-vendored upstream named in SURVEY.md section 8).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 OK, -1 bad argument/shape, -2 I/O or
+ *     parse error, -3 CUDA error, -4 capacity exceeded. coral_last_error() returns the
+ *     message for the calling thread. No exception crosses this boundary.
+ *   - pointers named *_dev are device pointers owned by the caller (e.g. torch tensors);
+ *     they are borrowed until the work queued on `stream` completes. `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream). All kernels are queued
+ *     asynchronously; the caller synchronises.
+ *   - handles (coral_lm, coral_decoder) are owned by the library, immutable after
+ *     creation except coral_decoder_set_params (caller serialises, as HF calls
+ *     reset_params before every decode). Per-decoder scratch in HBM grows lazily.
+ *   - strings cross the boundary as UTF-32 code points + int64 offsets ([n+1]).
+ */
+#ifndef CORAL_B200_H_
+#define CORAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct coral_lm coral_lm;
+typedef struct coral_decoder coral_decoder;
+
+#define CORAL_OK 0
+#define CORAL_EARG (-1)
+#define CORAL_EIO (-2)
+#define CORAL_ECUDA (-3)
+#define CORAL_ECAP (-4)
+
+#define CORAL_MAX_ORDER 6
+#define CORAL_MAX_VOCAB 64 /* alphabet entries (CoRal: 46) */
+
+const char* coral_last_error(void);
+int32_t coral_abi_version(void);
+
+/* ---------------------------------------------------------------- n-gram LM (A6/A8) */
+
+/* kenlm.Model(path) for an ARPA file (UP:kenlm python/kenlm.pyx; reached from
+ * R:src/coral/ngram.py:341-343 via pyctcdecode.build_ctcdecoder(kenlm_model_path=...)).
+ * Parses on the host and uploads the tables to `device`. */
+int32_t coral_lm_load_arpa(const char* path, int32_t device, coral_lm** out);
+int32_t coral_lm_free(coral_lm* lm);
+/* kenlm.Model.order, n-gram counts per order [order], vocabulary size, HBM bytes. */
+int32_t coral_lm_info(const coral_lm* lm, int32_t* order, uint64_t* ngram_counts, uint64_t* vocab_size,
+                      uint64_t* device_bytes);
+/* `word in kenlm_model` (UP:kenlm.pyx Model.__contains__): out[i] = vocabulary index != 0. */
+int32_t coral_lm_contains(const coral_lm* lm, const uint32_t* word_cps, const int64_t* word_offsets,
+                          int64_t n_words, int32_t* out);
+/* kenlm.Model.full_scores-style check of BaseScore on the DEVICE tables: sentences of
+ * words; out_probs gets one float32 log10 prob per word (+1 per sentence when eos),
+ * laid out at word_index + sentence_index*eos. Used by the parity tests of A8. */
+int32_t coral_lm_score_sentences(const coral_lm* lm, const uint32_t* word_cps_dev,
+                                 const int64_t* word_offsets_dev, const int64_t* sent_offsets_dev,
+                                 int64_t n_sentences, int32_t bos, int32_t eos, float* out_probs_dev,
+                                 int32_t* out_oov_dev, void* stream);
+
+/* ------------------------------------------------------------------- decoder (A5-A7) */
+
+/* pyctcdecode.build_ctcdecoder(labels, kenlm_model_path, unigrams, ...) after
+ * Alphabet.build_alphabet (R:src/coral/ngram.py:341-343). `labels` are the
+ * NORMALISED alphabet entries ("" blank, " " word delimiter) as UTF-32; lm may be NULL
+ * (no-LM mode); n_unigrams < 0 means unigrams=None. */
+int32_t coral_decoder_create(const uint32_t* label_cps, const int32_t* label_offsets, int32_t n_labels,
+                             int32_t blank_id, int32_t space_id, const coral_lm* lm,
+                             const uint32_t* unigram_cps, const int64_t* unigram_offsets, int64_t n_unigrams,
+                             int32_t device, coral_decoder** out);
+int32_t coral_decoder_free(coral_decoder* dec);
+/* BeamSearchDecoderCTC.reset_params / LanguageModel attributes
+ * (HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:365-367, :160-183). */
+int32_t coral_decoder_set_params(coral_decoder* dec, double alpha, double beta, double unk_score_offset,
+                                 int32_t score_boundary);
+/* HBM bytes held by the decoder (lexicon + scratch). */
+int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, uint64_t* device_bytes);
+
+/* BeamSearchDecoderCTC.decode_beams_batch / decode_batch over a padded batch
+ * (UP:pyctcdecode decoder.py; HF:...processing_wav2vec2_with_lm.py:398-406, :565-572;
+ * HF:pipelines/automatic_speech_recognition.py:612-616).
+ *   logits_dev   float32 [B, T_max, V]; rows >= lengths[b] are ignored
+ *   lengths_dev  int32 [B]
+ *   order_dev    int32 [B] processing order (longest first balances the tail) or NULL
+ *   input_mode   0 = pyctcdecode's auto-detection of probabilities vs logits, 1 logits, 2 probs
+ *   n_best       beams returned per utterance (<= beam_width)
+ * Outputs (device, caller-allocated):
+ *   out_n_beams     int32 [B]           number of final beams (<= beam_width)
+ *   out_logit_score float64 [B, n_best]
+ *   out_lm_score    float64 [B, n_best] combined score (pyctcdecode's "lm_score")
+ *   out_tokens      uint8 [B, n_best, T_max] alphabet indices of the text (no blanks)
+ *   out_lens        int32 [B, n_best]
+ *   out_status      int32 [B]           0 or CORAL_ECAP for that utterance
+ *   stats_dev       uint64 [8] or NULL: beam extensions, LM word scorings, n-gram probes,
+ *                   frames, lexicon probes (work counters of SURVEY 8d)
+ * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
+int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
+                              const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V,
+                              int32_t beam_width, double beam_prune_logp, double token_min_logp,
+                              int32_t prune_history, int32_t input_mode, int32_t n_best,
+                              int32_t* out_n_beams_dev, double* out_logit_score_dev, double* out_lm_score_dev,
+                              uint8_t* out_tokens_dev, int32_t* out_lens_dev, int32_t* out_status_dev,
+                              uint64_t* stats_dev, void* stream);
+
+/* -------------------------------------------------------------------- greedy (A3/A4) */
+
+/* np.argmax(axis=-1) + Wav2Vec2CTCTokenizer grouping (R:src/coral/compute_metrics.py:62-70;
+ * HF:models/wav2vec2/tokenization_wav2vec2.py:296-357, :410-459).
+ *   logits_dev     float32 [B, T_max, V]
+ *   lengths_dev    int32 [B] or NULL (= T_max for all)
+ *   pad_fixup      1: a frame whose V logits all equal -100 decodes to blank_id
+ *                  (R:src/coral/compute_metrics.py:66)
+ *   out_ids_dev    int32 [B, T_max] argmax per frame (first maximum wins) or NULL
+ *   out_tokens_dev int32 [B, T_max] ids after collapsing repeats and dropping blank_id
+ *   out_lens_dev   int32 [B] */
+int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, int32_t B, int32_t T_max,
+                         int32_t V, int32_t blank_id, int32_t pad_fixup, int32_t* out_ids_dev,
+                         int32_t* out_tokens_dev, int32_t* out_lens_dev, void* stream);
+/* Collapse already-decoded ids (the 2-D branch / label decoding with group_tokens on/off). */
+int32_t coral_ctc_collapse(const int32_t* ids_dev, const int32_t* lengths_dev, int32_t B, int32_t T_max,
+                           int32_t blank_id, int32_t group_tokens, int32_t* out_tokens_dev,
+                           int32_t* out_lens_dev, void* stream);
+
+/* ---------------------------------------------------------- edit counts (A1/A2/A11/A12) */
+
+#define CORAL_EDIT_TOKENS 0 /* sequences compared as given */
+#define CORAL_EDIT_CHARS 1  /* jiwer cer_default: Strip -> list of characters */
+#define CORAL_EDIT_WORDS 2  /* jiwer wer_default: RemoveMultipleSpaces -> Strip -> split(" ") */
+
+/* jiwer.process_characters / process_words -> rapidfuzz Levenshtein.editops counts
+ * (R:src/coral/metrics.py:26-33, :54-61).
+ *   out_sdih_dev   int32 [n_pairs, 4] = substitutions, deletions, insertions, hits
+ *   out_status_dev int32 [n_pairs]   1 when the reference is empty (jiwer raises ValueError)
+ *   max_len        upper bound on the code points of any one string (sizes on-chip buffers) */
+int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offsets_dev,
+                          const uint32_t* hyp_cps_dev, const int64_t* hyp_offsets_dev, int64_t n_pairs,
+                          int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,
+                          int32_t* out_status_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORAL_B200_H_ */

@@ -1,0 +1,66 @@
+"""Shared fixtures. ``-m "not gpu"`` runs on CPU (oracle, host logic, ABI exports, host
+simulation of the kernel logic); ``-m gpu`` tests are the parity tests proper and call the
+CUDA library through the C ABI. Nothing here reads /root/reference at run time."""
+
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CACHE = os.environ.get("CORAL_B200_CACHE", os.path.join(tempfile.gettempdir(), "coral_b200_cache"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def cache_dir():
+    os.makedirs(CACHE, exist_ok=True)
+    return CACHE
+
+
+@pytest.fixture(scope="session")
+def small_lm(cache_dir):
+    """(words, corpus model, ARPA path) of a small 4-gram LM (2k words, 5k sentences)."""
+    from coral_b200 import synth
+
+    return synth.build_lm(cache_dir, order=4, n_words=2000, n_sent=5000)
+
+
+@pytest.fixture(scope="session")
+def small_workload(cache_dir, small_lm):
+    from coral_b200 import synth
+
+    return synth.build_workload(cache_dir, 12, order=4, n_words=2000, n_sent=5000, name="t")
+
+
+@pytest.fixture(scope="session")
+def oracle_decoder(small_lm):
+    from coral_b200 import synth
+    from oracle.beam import build_ctcdecoder
+
+    return build_ctcdecoder(synth.CORAL_LABELS, small_lm[2])
+
+
+def beams_equal(ref_beams, got_beams, rel=1e-4):
+    """ref: oracle 5-tuples; got: (text, ..., logit, lm) with scores at [-2], [-1]."""
+    assert len(ref_beams) == len(got_beams), (len(ref_beams), len(got_beams))
+    for i, (r, g) in enumerate(zip(ref_beams, got_beams)):
+        assert r[0] == g[0], f"beam {i}: {r[0]!r} != {g[0]!r}"
+        assert abs(r[-2] - g[-2]) <= rel * max(1.0, abs(r[-2])), (i, r[-2], g[-2])
+        assert abs(r[-1] - g[-1]) <= rel * max(1.0, abs(r[-1])), (i, r[-1], g[-1])
+
+
+@pytest.fixture(scope="session")
+def rng():
+    return np.random.default_rng(20261017)

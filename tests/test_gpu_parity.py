@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs. Integer / byte / index results are bit-exact; beam-search
+transcripts identical with scores within 1e-4 relative (the tolerance BASELINE.json states)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import beams_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def gpu_decoder(small_lm, torch_cuda):
+    from coral_b200 import synth
+    from coral_b200.decoder import build_ctcdecoder
+
+    return build_ctcdecoder(synth.CORAL_LABELS, small_lm[2])
+
+
+@pytest.fixture(scope="module")
+def coral_vocab():
+    from coral_b200.greedy import CTCVocabulary
+    from oracle.greedy import CORAL_PAD_ID, CORAL_VOCAB
+
+    return CTCVocabulary(CORAL_VOCAB, CORAL_PAD_ID)
+
+
+# ------------------------------------------------------------------------------ greedy
+def test_greedy_matches_numpy_argmax_and_tokenizer_rules(torch_cuda, coral_vocab, rng):
+    from coral_b200.greedy import greedy_decode_device
+    from oracle.greedy import ids_to_string
+
+    torch = torch_cuda
+    B, T, V = 64, 499, 46  # config 1 of BASELINE.json
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    # exact ties (first maximum must win), special tokens winning, and repeated frames
+    logits[0, :50, 3] = logits[0, :50, 7] = 9.0
+    logits[1, :40, 42] = 12.0
+    logits[2, 10:60] = logits[2, 10]
+    lengths = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lengths[3] = T
+    d = torch.from_numpy(logits).cuda()
+    ids, tokens, lens = greedy_decode_device(d, torch.from_numpy(lengths).cuda(), blank_id=45, want_ids=True)
+    ids, tokens, lens = ids.cpu().numpy(), tokens.cpu().numpy(), lens.cpu().numpy()
+    ref_ids = np.argmax(logits, axis=-1)
+    got = coral_vocab.to_strings(tokens, lens)
+    for b in range(B):
+        assert np.array_equal(ids[b, : lengths[b]], ref_ids[b, : lengths[b]])
+        assert got[b] == ids_to_string(ref_ids[b, : lengths[b]])
+
+
+def test_compute_error_rate_metrics_matches_oracle(torch_cuda, rng):
+    from types import SimpleNamespace
+
+    from coral_b200.compute_metrics import compute_error_rate_metrics
+    from oracle import greedy as og
+
+    B, T, V = 16, 120, 46
+    preds = (rng.standard_normal((B, T, V)) * 3).astype(np.float32)
+    preds[:, 80:, :] = -100.0  # Trainer pads the time axis with -100 (HF:trainer.py:2678-2722)
+    preds[5, 40:, :] = -100.0
+    labels = rng.integers(0, 42, size=(B, 30)).astype(np.int64)
+    labels[:, 20:] = -100
+    labels[:, 5] = 36
+    labels[:, 12] = 36
+
+    class Tok:
+        pad_token_id = 45
+        word_delimiter_token = "|"
+        unk_token = "<unk>"
+        do_lower_case = False
+
+        def get_vocab(self):
+            return {t: i for i, t in enumerate(og.CORAL_VOCAB)}
+
+    ref = og.compute_error_rate_metrics(preds, labels)
+    lab2 = labels.copy()
+    got = compute_error_rate_metrics(SimpleNamespace(predictions=preds.copy(), label_ids=lab2),
+                                     SimpleNamespace(tokenizer=Tok()), log_examples=False)
+    assert got == ref
+    assert (lab2 != -100).all()  # same in-place fix-up as R:src/coral/compute_metrics.py:46-48
+
+
+# -------------------------------------------------------------------------------- edit
+def _random_pairs(rng, n, alphabet, max_len, p_ws=0.15):
+    refs, hyps = [], []
+    for _ in range(n):
+        L = int(rng.integers(1, max_len))
+        ref = "".join(rng.choice(list(alphabet), size=L))
+        if not ref.strip():
+            ref = "a" + ref
+        h = list(ref)
+        for _ in range(int(rng.integers(0, max(2, L // 4)))):
+            k = int(rng.integers(0, 3))
+            pos = int(rng.integers(0, len(h) + 1))
+            if k == 0 and h:
+                h[min(pos, len(h) - 1)] = str(rng.choice(list(alphabet)))
+            elif k == 1 and h:
+                del h[min(pos, len(h) - 1)]
+            else:
+                h.insert(pos, str(rng.choice(list(alphabet))))
+        refs.append(ref)
+        hyps.append("".join(h))
+    return refs, hyps
+
+
+@pytest.mark.parametrize("max_len", [40, 128, 300, 700])
+def test_edit_counts_bit_exact(torch_cuda, rng, max_len):
+    from coral_b200.metrics import edit_counts
+    from oracle import edit as oe
+
+    n = 400 if max_len <= 128 else 60
+    refs, hyps = _random_pairs(rng, n, "abcdeæøå  \t", max_len)
+    hyps[0] = ""                      # empty hypothesis: all deletions
+    hyps[1] = refs[1]                 # identical
+    refs[2], hyps[2] = "ab", "ba"     # SURVEY known answer (0, 1, 1)
+    refs[3], hyps[3] = "hej med dig", "hej  med   dig"
+    cc = edit_counts(hyps, refs, "chars")
+    wc = edit_counts(hyps, refs, "words")
+    for i in range(n):
+        assert tuple(cc[i]) == oe.char_counts(refs[i], hyps[i]), (i, refs[i], hyps[i])
+        assert tuple(wc[i]) == oe.word_counts(refs[i], hyps[i]), (i, refs[i], hyps[i])
+    assert tuple(cc[2][:3]) == (0, 1, 1)
+
+
+def test_cer_wer_and_errors(torch_cuda, rng):
+    from coral_b200 import metrics
+    from oracle import edit as oe
+
+    refs, hyps = _random_pairs(rng, 300, "abcdefg hij", 60)
+    for norm in (True, False):
+        assert metrics.cer(hyps, refs, norm) == oe.cer(hyps, refs, norm)
+        assert metrics.wer(hyps, refs, norm) == oe.wer(hyps, refs, norm)
+    with pytest.raises(ValueError):
+        metrics.cer(["abc"], [""])
+    with pytest.raises(ValueError):
+        metrics.wer(["abc"], ["   "])
+    with pytest.raises(ZeroDivisionError):
+        metrics.cer([], [])
+
+
+def test_get_score_df_and_validation(torch_cuda, rng):
+    import pandas as pd
+
+    from coral_b200.evaluate import get_score_df
+    from coral_b200.validation import validation_scores
+    from oracle import edit as oe
+
+    refs, hyps = _random_pairs(rng, 240, "abcdefg hij", 50)
+    df = pd.DataFrame(dict(
+        age_group=rng.choice(["0-25", "25-50", "50+"], size=240),
+        gender=rng.choice(["female", "male"], size=240),
+        dialect=rng.choice(["a", "b", "c", "d"], size=240),
+        prediction=hyps, text=refs))
+    got = get_score_df(df, ["age_group", "gender", "dialect"])
+    ref = oe.get_score_records(df.to_dict("records"), ["age_group", "gender", "dialect"])
+    # same records, same order; exact float equality (integer counts -> one division)
+    pd.testing.assert_frame_equal(got, pd.DataFrame.from_records(ref), check_exact=True)
+    vs = validation_scores(hyps, refs, max_cer=0.6)
+    assert vs.cer == oe.cer(hyps, refs) and vs.wer == oe.wer(hyps, refs)
+    assert np.array_equal(vs.asr_cer, np.array(oe.per_sample_rates(hyps, refs, True, "cer")))
+    assert np.array_equal(vs.keep, vs.asr_cer < 0.6)
+
+
+# ---------------------------------------------------------------------------------- LM
+def test_device_lm_scores_bit_exact(gpu_decoder, oracle_decoder, small_lm, rng):
+    from coral_b200 import synth
+
+    words, model, _ = small_lm
+    flat, lens = model.sample(300, "lmtest")
+    sents = [s.split(" ") for s in synth.sentences_to_text(flat, lens, words)]
+    for s in sents[::3]:
+        s[int(rng.integers(len(s)))] = "zzzoov"
+    km = gpu_decoder._language_model.kenlm_model
+    m = oracle_decoder._language_model._kenlm_model
+    assert km.order == m.order and ("zzzoov" in km) is False and (words[0] in km) == (words[0] in m)
+    for bos, eos in ((True, True), (False, False)):
+        probs, oovs = km.score_sentences(sents, bos=bos, eos=eos)
+        for s, p, o in zip(sents, probs, oovs):
+            st = m.begin_sentence_state() if bos else m.null_context_state()
+            ref = []
+            for w in s:
+                x, st = m.base_score(st, w)
+                ref.append(x)
+            if eos:
+                ref.append(m.base_score(st, "</s>")[0])
+            assert np.array_equal(np.array(ref, dtype=np.float32), p)
+            assert [int(w not in m) for w in s] == o.tolist()
+
+
+# -------------------------------------------------------------------------------- beam
+def test_beam_search_peaky_all_beams(gpu_decoder, oracle_decoder, small_workload):
+    w = small_workload
+    lg = [w.logits[u, : w.lengths[u]] for u in range(len(w.lengths))]
+    got = gpu_decoder.decode_beams_batch(None, lg)
+    for u in range(len(lg)):
+        ref = oracle_decoder.decode_beams(lg[u])
+        beams_equal(ref, got[u])
+    assert gpu_decoder.decode_batch(None, lg) == [oracle_decoder.decode(x) for x in lg]
+    assert gpu_decoder.decode(lg[0]) == oracle_decoder.decode(lg[0])
+    b5 = gpu_decoder.decode_beams(lg[1])
+    assert len(b5[0]) == 5 and b5[0][0] == oracle_decoder.decode(lg[1])
+
+
+@pytest.mark.parametrize("beam_width,T", [(16, 80), (100, 60), (200, 40), (512, 24)])
+def test_beam_search_flat_logits_trim_path(gpu_decoder, oracle_decoder, rng, beam_width, T):
+    from coral_b200 import synth
+
+    lg = [synth.flat_logits(T, rng), synth.flat_logits(max(1, T // 2), rng)]
+    got = gpu_decoder.decode_beams_batch(None, lg, beam_width=beam_width)
+    for x, g in zip(lg, got):
+        beams_equal(oracle_decoder.decode_beams(x, beam_width=beam_width), g)
+
+
+def test_beam_search_parameters(gpu_decoder, oracle_decoder, small_workload):
+    w = small_workload
+    lg = [w.logits[u, : w.lengths[u]] for u in range(4)]
+    cases = [
+        dict(beam_width=25, beam_prune_logp=-5.0, token_min_logp=-3.0),
+        dict(beam_width=64, beam_prune_logp=-20.0, token_min_logp=-10.0),
+        dict(beam_width=128, beam_prune_logp=-10.0, token_min_logp=-20.0),
+    ]
+    for kw in cases:
+        got = gpu_decoder.decode_beams_batch(None, lg, **kw)
+        for x, g in zip(lg, got):
+            beams_equal(oracle_decoder.decode_beams(x, **kw), g)
+    try:
+        for dec in (gpu_decoder, oracle_decoder):
+            dec.reset_params(alpha=0.9, beta=0.3, unk_score_offset=-4.0, lm_score_boundary=False)
+        got = gpu_decoder.decode_beams_batch(None, lg)
+        for x, g in zip(lg, got):
+            beams_equal(oracle_decoder.decode_beams(x), g)
+    finally:
+        for dec in (gpu_decoder, oracle_decoder):
+            dec.reset_params(alpha=0.5, beta=1.5, unk_score_offset=-10.0, lm_score_boundary=True)
+
+
+def test_beam_search_no_lm_edge_cases_and_errors(torch_cuda, small_workload, rng):
+    from coral_b200 import synth
+    from coral_b200.decoder import build_ctcdecoder
+    from oracle.beam import build_ctcdecoder as oracle_build
+
+    g = build_ctcdecoder(synth.CORAL_LABELS)
+    o = oracle_build(synth.CORAL_LABELS)
+    w = small_workload
+    lg = [w.logits[0, : w.lengths[0]], synth.flat_logits(30, rng), w.logits[1, :1],
+          np.zeros((0, 46), np.float32)]
+    got = g.decode_beams_batch(None, lg)
+    for x, gb in zip(lg, got):
+        beams_equal(o.decode_beams(x), gb)
+    # probabilities instead of logits (pyctcdecode's auto-detection)
+    z = w.logits[2, : w.lengths[2]].astype(np.float64)
+    p = np.exp(z - z.max(axis=1, keepdims=True))
+    p = (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+    import math
+    if math.isclose(float(p.sum(axis=1).mean()), 1):
+        beams_equal(o.decode_beams(p), g.decode_beams_batch(None, [p])[0])
+    with pytest.raises(ValueError):
+        g.decode_beams(np.zeros((10, 40), np.float32))
+    with pytest.raises(ValueError):
+        g.decode_beams(np.zeros((2, 10, 46), np.float32))
+    with pytest.raises(NotImplementedError):
+        g.decode_beams(lg[0], hotwords=["hej"])
+
+
+def test_hf_processor_with_lm_drop_in(gpu_decoder, oracle_decoder, small_workload, tmp_path):
+    """The unmodified HF Wav2Vec2ProcessorWithLM drives the CUDA decoder through the shims."""
+    import json
+
+    import multiprocessing
+
+    import coral_b200
+
+    coral_b200.install_shims()
+    # HF forks a Pool around decode_beams_batch when the start method is "fork"
+    # (HF:...processing_wav2vec2_with_lm.py:374-389); with "spawn" it decodes in-process.
+    multiprocessing.set_start_method("spawn", force=True)
+    from transformers import Wav2Vec2CTCTokenizer, Wav2Vec2FeatureExtractor, Wav2Vec2ProcessorWithLM
+
+    from coral_b200 import synth
+
+    vocab = {c: i for i, c in enumerate(synth.CORAL_LABELS[:42])}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    tok = Wav2Vec2CTCTokenizer(str(tmp_path / "vocab.json"), unk_token="<unk>", pad_token="<pad>",
+                               bos_token="<s>", eos_token="</s>", word_delimiter_token="|")
+    fe = Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True)
+    proc = Wav2Vec2ProcessorWithLM(feature_extractor=fe, tokenizer=tok, decoder=gpu_decoder)
+    w = small_workload
+    out = proc.batch_decode(w.logits[:6])  # padded with -100 rows; HF strips them (:371)
+    ref = [oracle_decoder.decode_beams(w.logits[u, : w.lengths[u]])[0] for u in range(6)]
+    assert out.text == [r[0] for r in ref]
+    for a, r in zip(out.logit_score, ref):
+        assert abs(a - r[3]) <= 1e-4 * max(1, abs(r[3]))
+    one = proc.decode(w.logits[0, : w.lengths[0]])
+    assert one.text == ref[0][0]
+    # round trip through pyctcdecode's directory layout
+    proc.save_pretrained(str(tmp_path / "m"))
+    assert (tmp_path / "m" / "alphabet.json").exists() and (tmp_path / "m" / "language_model" / "attrs.json").exists()
+    proc2 = Wav2Vec2ProcessorWithLM.from_pretrained(str(tmp_path / "m"))
+    assert proc2.batch_decode(w.logits[:3]).text == out.text[:3]
+
+
+def test_full_size_properties(gpu_decoder, torch_cuda, cache_dir, rng):
+    """Size-independent properties at a larger batch: determinism across launches and slot
+    reuse, n_best=1 equals the head of the full beam list, identical inputs give identical
+    outputs wherever they sit in the batch."""
+    from coral_b200 import synth
+
+    w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
+    a = gpu_decoder.decode_padded(w.logits, w.lengths, n_best=1, collect_stats=True)
+    b = gpu_decoder.decode_padded(w.logits, w.lengths, n_best=1)
+    assert np.array_equal(a.tokens, b.tokens) and np.array_equal(a.logit_score, b.logit_score)
+    assert a.stats[3] == int(w.lengths.sum())  # every frame was processed exactly once
+    perm = rng.permutation(256)
+    c = gpu_decoder.decode_padded(w.logits[perm], w.lengths[perm], n_best=1)
+    assert np.array_equal(c.lens[:, 0], a.lens[perm, 0]) and np.array_equal(c.lm_score, a.lm_score[perm])
+    full = gpu_decoder.decode_padded(w.logits[:32], w.lengths[:32], n_best=100)
+    assert np.array_equal(full.lm_score[:, 0], a.lm_score[:32, 0])
+    assert (np.diff(full.lm_score, axis=1)[np.arange(100)[None, 1:] < full.n_beams[:, None]] <= 0).all()
