@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched CTC prefix beam search (beam 100, 5-gram LM shallow
+fusion) + WER/CER scoring, on synthetic logits of the shape BASELINE.json names.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...           # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch: decode every utterance of the shard
+(auto input detection + beam search kernel), turn the winning token rows into code points
+on the device, score them against the references (chars + words edit-count kernels), sum
+the counts and -- for N > 1 -- all-reduce them over NCCL. Workload = BASELINE.json
+configs[1]: read-aloud-shaped utterances (T in [24, 499], mean ~290 frames), trained-model-
+like ("peaky") logits, V = 46, beam 100, beam_prune_logp -10, token_min_logp -5, 5-gram ARPA
+LM over a synthetic Danish-charset corpus. Weak scaling: every rank owns a full shard.
+
+`value`   utterances/s with the inputs resident in HBM (CUDA events, max over ranks)
+`e2e`     the same metric through the public API with HOST inputs: pinned logits -> H2D ->
+          decode -> D2H tokens -> Python strings -> cer()/wer() (their H2D/D2H inside)
+`roofline` for the beam-search kernel: algorithmic bytes / its CUDA-event time
+`cpu_baseline` the oracle (a port of pyctcdecode+KenLM+jiwer, which are not installable
+          here) timed on this box's host cores on a bounded sample of the same workload
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded utterances/sec (prefix beam search beam=100 + 5-gram LM fusion + WER/CER scoring)"
+UNIT = "utterances/s"
+CACHE = os.environ.get("CORAL_B200_CACHE", os.path.join(tempfile.gettempdir(), "coral_b200_cache"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=8192, help="utterances per GPU per step")
+    ap.add_argument("--beam", type=int, default=100)
+    ap.add_argument("--order", type=int, default=5)
+    ap.add_argument("--kind", default="peaky", choices=["peaky", "flat"])
+    ap.add_argument("--shape", default="read_aloud", choices=["read_aloud", "conversation"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- CPU side
+_ORACLE = {}
+
+
+def _oracle_init(labels, arpa):
+    from oracle.beam import build_ctcdecoder
+
+    _ORACLE["dec"] = build_ctcdecoder(labels, arpa)
+
+
+def _oracle_decode(args):
+    logits, beam = args
+    dec = _ORACLE["dec"]
+    s0 = dict(dec.stats)
+    text = dec.decode_beams(logits, beam_width=beam)[0][0]
+    d = {k: dec.stats[k] - s0[k] for k in s0}
+    return text, d
+
+
+def cpu_reference_pass(wl, idx, beam, n_procs, pool=None):
+    """The reference's CPU path on utterances ``idx``: pyctcdecode-style beam search with the
+    KenLM-semantics scorer, fork pool over utterances like
+    HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:374-406, then cer()/wer()
+    one pair at a time like R:src/coral/metrics.py:26-33. Returns (seconds, stats, hyps)."""
+    from oracle import edit as oracle_edit
+
+    items = [(wl.logits[u, : wl.lengths[u]], beam) for u in idx]
+    t0 = time.perf_counter()
+    if pool is None:
+        out = [_oracle_decode(it) for it in items]
+    else:
+        out = pool.map(_oracle_decode, items, chunksize=max(1, len(items) // (4 * n_procs)))
+    hyps = [o[0] for o in out]
+    refs = [wl.references[u] for u in idx]
+    c = oracle_edit.cer(hyps, refs)
+    w = oracle_edit.wer(hyps, refs)
+    dt = time.perf_counter() - t0
+    stats = {}
+    for _, d in out:
+        for k, v in d.items():
+            stats[k] = stats.get(k, 0) + v
+    stats["cer"], stats["wer"] = c, w
+    return dt, stats, hyps
+
+
+def make_pool(wl, n_procs):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    return ctx.Pool(n_procs, initializer=_oracle_init, initargs=(wl.labels, wl.arpa_path))
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from coral_b200 import synth
+
+    n_procs = os.cpu_count() or 1
+    sample = args.cpu_sample or 16 * n_procs
+    wl = synth.build_workload(CACHE, sample, order=args.order, kind=args.kind, shape=args.shape, name="eval0")
+    idx = list(range(sample))
+    pool = make_pool(wl, n_procs)
+    try:
+        for _ in range(max(args.warmup, 1)):
+            cpu_reference_pass(wl, idx[: max(n_procs, sample // 4)], args.beam, n_procs, pool)
+        times = []
+        for _ in range(args.steps):
+            dt, stats, _ = cpu_reference_pass(wl, idx, args.beam, n_procs, pool)
+            times.append(dt)
+    finally:
+        pool.close()
+        pool.join()
+    total = sum(times)
+    value = sample * args.steps / total
+    audio = float(synth.audio_seconds(wl.lengths).sum())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 log-probs / f64 scores / int32 counts",
+        "data": "synthetic",
+        "config": workload_config(args, sample, "bounded sample of the same workload; CPU only"),
+        "audio_s_per_s": audio * args.steps / total,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_procs, "kind": "port",
+                         "sample": f"{sample} utterances per step, fork pool of {n_procs} processes over utterances "
+                                   "(oracle port of pyctcdecode 0.5.0 + KenLM + jiwer; the real packages are not "
+                                   "installable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, utts, note):
+    return {
+        "workload": f"BASELINE configs[1]: {args.shape} {args.kind} logits [B,T<=499,46], beam={args.beam}, "
+                    f"beam_prune_logp=-10, token_min_logp=-5, {args.order}-gram ARPA LM (50k words, 200k sentences), "
+                    "alpha=0.5 beta=1.5 unk=-10, + CER/WER vs references",
+        "utterances_per_gpu_per_step": utts, "beam_width": args.beam, "lm_order": args.order, "logits": args.kind,
+        "l2": "inputs larger than L2 (logits of one step: %.0f MB per GPU)" % (utts * 499 * 46 * 4 / 1e6),
+        "note": note,
+    }
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from coral_b200 import metrics, synth
+    from coral_b200.decoder import build_ctcdecoder
+    from coral_b200.textio import encode_utf32
+
+    # ---- CPU baseline first (rank 0, N = 1 only), before this process touches CUDA
+    cpu_baseline = None
+    oracle_stats = None
+    wl = synth.build_workload(CACHE, args.utts, order=args.order, kind=args.kind, shape=args.shape,
+                              name=f"eval{rank}")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_procs = os.cpu_count() or 1
+        sample = args.cpu_sample or 16 * n_procs
+        sample = min(sample, args.utts)
+        idx = list(range(sample))
+        pool = make_pool(wl, n_procs)
+        try:
+            cpu_reference_pass(wl, idx[:n_procs], args.beam, n_procs, pool)  # warm the workers
+            dt, oracle_stats, cpu_hyps = cpu_reference_pass(wl, idx, args.beam, n_procs, pool)
+        finally:
+            pool.close()
+            pool.join()
+        _oracle_init(wl.labels, wl.arpa_path)
+        t0 = time.perf_counter()
+        seq_n = min(sample, 2 * n_procs)
+        for u in idx[:seq_n]:
+            _oracle_decode((wl.logits[u, : wl.lengths[u]], args.beam))
+        seq_rate = seq_n / (time.perf_counter() - t0)
+        cpu_baseline = {
+            "value": sample / dt, "unit": UNIT, "cores": n_procs, "kind": "port",
+            "sample": f"first {sample} utterances of the workload, fork pool of {n_procs} processes over utterances "
+                      f"(HF batch_decode regime) + cer/wer; sequential single-process regime (what evaluate() does): "
+                      f"{seq_rate:.1f} utt/s; oracle port -- pyctcdecode/kenlm/jiwer are not installable here",
+        }
+        oracle_stats["sample"] = sample
+        oracle_stats["hyps"] = cpu_hyps
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dec = build_ctcdecoder(wl.labels, wl.arpa_path)
+    B = args.utts
+    Tm = wl.logits.shape[1]
+    h_logits = torch.from_numpy(wl.logits).pin_memory()
+    h_len = torch.from_numpy(wl.lengths).pin_memory()
+    d_logits = h_logits.to(dev)
+    d_len = h_len.to(dev)
+    refs = wl.references
+    r_cps, r_off = encode_utf32(refs)
+    d_rcps = torch.from_numpy(r_cps.view(np.int32)).to(dev)
+    d_roff = torch.from_numpy(r_off).to(dev)
+    d_rbeg, d_rend = d_roff[:-1].contiguous(), d_roff[1:].contiguous()
+    max_len = int(max(np.diff(r_off).max(), Tm))
+    cp_table = torch.from_numpy(dec._cp_table.astype(np.int64)).to(dev).to(torch.int32)
+    d_hbeg = (torch.arange(B, device=dev, dtype=torch.int64) * Tm).contiguous()
+    kern_ms = []
+
+    def step_device(time_kernel=False):
+        """Inputs resident in HBM; everything stays on the device."""
+        if time_kernel:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # decode_padded: argsort of lengths (torch) + classify kernel + beam-search kernel
+        d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+        outs = dec.decode_launch(d_logits, d_len, d_order, beam_width=args.beam, n_best=1,
+                                 events=(e0, e1) if time_kernel else None)
+        d_n, d_logit, d_comb, d_tok, d_lens, d_status = outs
+        hyp_cps = cp_table[d_tok.view(B, Tm).to(torch.int64)]
+        d_hend = d_hbeg + d_lens.view(B).to(torch.int64)
+        cc, _ = metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps, d_hbeg, d_hend, B, 1, max_len)
+        wc, _ = metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps, d_hbeg, d_hend, B, 2, max_len)
+        totals = torch.stack([cc.sum(dim=0, dtype=torch.int64), wc.sum(dim=0, dtype=torch.int64)])
+        if world > 1:
+            dist.all_reduce(totals)
+        if time_kernel:
+            kern_ms.append((e0, e1))
+        return totals, d_status
+
+    def step_e2e():
+        """Public API with host inputs: H2D of the logits, decode, D2H, strings, cer/wer."""
+        hyps = dec.decode_batch(None, h_logits, beam_width=args.beam, lengths=h_len)
+        if world > 1:
+            from coral_b200.sharded import sharded_error_rates
+
+            r = sharded_error_rates(hyps, refs)
+            return hyps, r["cer"], r["wer"]
+        return hyps, metrics.cer(hyps, refs), metrics.wer(hyps, refs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate on the CPU sample before any timing is reported
+    hyps, cer_v, wer_v = step_e2e()
+    parity = None
+    if oracle_stats is not None:
+        s = oracle_stats["sample"]
+        same = hyps[:s] == oracle_stats["hyps"]
+        from oracle import edit as oracle_edit
+
+        same_counts = (metrics.cer(hyps[:s], refs[:s]) == oracle_edit.cer(hyps[:s], refs[:s]) and
+                       metrics.wer(hyps[:s], refs[:s]) == oracle_edit.wer(hyps[:s], refs[:s]))
+        parity = {"transcripts_identical": bool(same), "cer_wer_bit_exact": bool(same_counts), "sample": s}
+        if not (same and same_counts):
+            raise SystemExit(f"PARITY FAILURE against the oracle on the CPU sample: {parity}")
+
+    # ---- timed: device-resident
+    for _ in range(max(args.warmup, 3)):
+        totals, d_status = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        totals, d_status = step_device(time_kernel=True)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    beam_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+    assert int(d_status.sum().item()) == 0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # ---- timed: end to end through the public API
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        hyps, cer_v, wer_v = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    # ---- work counters (one extra untimed launch with stats)
+    st = dec.decode_padded(d_logits, d_len, beam_width=args.beam, n_best=1, collect_stats=True).stats
+
+    if rank == 0:
+        frames = int(wl.lengths.sum())
+        audio = float(synth.audio_seconds(wl.lengths).sum())
+        hyp_chars = int(sum(len(h) for h in hyps))
+        # algorithmic bytes of the beam kernel: logits once + LM slots + output
+        alg_logits = frames * 46 * 4
+        if oracle_stats is not None:
+            s = oracle_stats["sample"]
+            scale = B / s
+            n_score, probes, n_partial = (oracle_stats[k] * scale for k in ("n_score", "probes", "n_partial"))
+            lm_src = f"oracle cache-miss counts on the {s}-utterance CPU sample, scaled to {B}"
+        else:
+            n_score, probes, n_partial = float(st[1]), float(st[2]), float(st[4])
+            lm_src = "device counters (no CPU sample in this run)"
+        alg_lm = probes * 16 + n_score * 16 + n_partial * 8
+        alg_out = hyp_chars + 16 * B
+        alg_bytes = alg_logits + alg_lm + alg_out
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "beam_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        achieved = alg_bytes / (beam_ms * 1e-3) / 1e9
+        e2e_value = world * B * e2e_steps / e2e_s
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 log-probs / f64 beam scores / int32 edit counts", "data": "synthetic",
+            "config": workload_config(args, B, "value: inputs resident in HBM; e2e: host logits through decode_batch + cer/wer"),
+            "audio_s_per_s": world * audio * args.steps / (dev_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h_logits.numel() * 4 + B * 4 + 2 * (r_cps.nbytes + r_off.nbytes) + 2 * (hyp_chars * 4 + 8 * (B + 1))),
+                    "d2h_bytes_per_step": int(B * Tm + B * (4 + 8 + 8 + 4 + 4) + 2 * B * 20),
+                    "audio_s_per_s": world * audio * e2e_steps / e2e_s, "steps": e2e_steps},
+            "gpu_launches": 4 * args.steps,
+            "kernels_per_step": ["classify_input_kernel", "beam_search_kernel", "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
+            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<32,128,320> (+ classify_input_kernel, same event pair)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "algorithmic_bytes_breakdown": {"logits": alg_logits, "lm_slots": alg_lm, "output": alg_out, "lm_counts_from": lm_src},
+                         "kernel_ms_per_launch": beam_ms,
+                         "note": "latency-bound by construction (SURVEY 7.6): T sequential frames per utterance; "
+                                 "see beam_extensions_per_s and profiles/ for stall reasons"},
+            "beam_extensions_per_s": float(st[0]) / (beam_ms * 1e-3),
+            "device_counters_per_step": {"beam_extensions": int(st[0]), "lm_word_scorings": int(st[1]),
+                                         "ngram_probes": int(st[2]), "frames": int(st[3]), "lexicon_probes": int(st[4])},
+            "cpu_baseline": cpu_baseline,
+            "parity_gate": parity,
+            "quality": {"cer": cer_v, "wer": wer_v},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ SIGNATURES = {
     "coral_ctc_greedy": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "coral_ctc_collapse": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "coral_edit_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "coral_edit_counts_spans": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
 }
 
 

@@ -2,6 +2,7 @@
 // The per-utterance algorithm lives in beam_core.h; this file owns the persistent
 // kernel (one thread group per utterance at a time, work-stealing over the batch),
 // the HBM scratch arenas and pyctcdecode's probabilities-vs-logits detection.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -394,11 +395,29 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
     L.is_prob = dec->d_is_prob;
   }
 
-  if (beam_width <= 32) return launch_beam<32, 32, 128>(dec, L, B, st);
-  if (beam_width <= 64) return launch_beam<32, 64, 192>(dec, L, B, st);
-  if (beam_width <= 128) return launch_beam<32, 128, 320>(dec, L, B, st);
-  if (beam_width <= 256) return launch_beam<64, 256, 640>(dec, L, B, st);
-  return launch_beam<128, 512, 1280>(dec, L, B, st);
+  // threads per utterance: CORAL_BEAM_NT overrides the default (tuning knob)
+  int nt = 0;
+  if (const char* e = getenv("CORAL_BEAM_NT")) nt = atoi(e);
+  if (beam_width <= 32) {
+    if (nt == 64) return launch_beam<64, 32, 128>(dec, L, B, st);
+    return launch_beam<32, 32, 128>(dec, L, B, st);
+  }
+  if (beam_width <= 64) {
+    if (nt == 32) return launch_beam<32, 64, 192>(dec, L, B, st);
+    if (nt == 128) return launch_beam<128, 64, 192>(dec, L, B, st);
+    return launch_beam<64, 64, 192>(dec, L, B, st);
+  }
+  if (beam_width <= 128) {
+    if (nt == 32) return launch_beam<32, 128, 320>(dec, L, B, st);
+    if (nt == 64) return launch_beam<64, 128, 320>(dec, L, B, st);
+    if (nt == 256) return launch_beam<256, 128, 320>(dec, L, B, st);
+    return launch_beam<128, 128, 320>(dec, L, B, st);
+  }
+  if (beam_width <= 256) {
+    if (nt == 128) return launch_beam<128, 256, 640>(dec, L, B, st);
+    return launch_beam<256, 256, 640>(dec, L, B, st);
+  }
+  return launch_beam<256, 512, 1280>(dec, L, B, st);
 }
 
 }  // extern "C"

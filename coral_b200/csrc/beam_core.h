@@ -169,7 +169,7 @@ struct UttIO {
   uint8_t* out_tokens;  // [n_best, T_max]
   int32_t* out_len;     // [n_best]
   int32_t* out_status;  // scalar: 0 ok, -4 capacity
-  unsigned long long* stats;  // optional [4]: extensions, lm scorings, lexicon probes, frames
+  unsigned long long* stats;  // optional [8]: extensions, LM scorings, n-gram probes, frames, lexicon probes
 };
 
 template <int BW, int OUTC>
@@ -535,7 +535,7 @@ struct BeamDecoder {
                   unsigned long long h = sm.whash[cur][rb];
                   for (int q = 0; q < P.label_ncp[c]; ++q) h = word_hash_push(h, P.label_cps[c][q]);
                   uint32_t lw, lf;
-                  if (io.stats) atom_add(&io.stats[2], 1ULL);
+                  if (io.stats) atom_add(&io.stats[4], 1ULL);
                   if (lex_find(lm, h, lw, lf)) {
                     nfl = ((lf & kLexPrefixOfUnigram) ? 0u : kOovPartial) | ((lf & kLexInUnigrams) ? kInUni : 0u) |
                           ((lf & kLexInLm) ? kInLm : 0u);

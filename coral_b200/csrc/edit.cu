@@ -92,8 +92,9 @@ __device__ int split_words(const uint32_t* cps, int64_t s, int64_t e, int lane, 
 
 template <bool GLOBAL_WORK, int LCAP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restrict__ ref_off,
-                   const uint32_t* __restrict__ hyp_cps, const int64_t* __restrict__ hyp_off, int64_t n_pairs,
+edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restrict__ ref_beg,
+                   const int64_t* __restrict__ ref_end, const uint32_t* __restrict__ hyp_cps,
+                   const int64_t* __restrict__ hyp_beg, const int64_t* __restrict__ hyp_end, int64_t n_pairs,
                    int mode, int32_t* __restrict__ out_sdih, int32_t* __restrict__ out_status, uint8_t* gwork,
                    size_t gwork_stride, int gcap) {
   constexpr int SCAP = GLOBAL_WORK ? 32 : LCAP;
@@ -122,8 +123,8 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
   }
   for (int64_t pair = gw; pair < n_pairs; pair += nwarps) {
     __syncwarp();
-    const int64_t r0 = ref_off[pair], r1 = ref_off[pair + 1];
-    const int64_t h0 = hyp_off[pair], h1 = hyp_off[pair + 1];
+    const int64_t r0 = ref_beg[pair], r1 = ref_end[pair];
+    const int64_t h0 = hyp_beg[pair], h1 = hyp_end[pair];
     int n1 = 0, n2 = 0;
     int status = (r1 == r0) ? 1 : 0;
     if (mode == CORAL_EDIT_TOKENS) {
@@ -278,13 +279,15 @@ using namespace coral;
 
 extern "C" {
 
-int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offsets_dev, const uint32_t* hyp_cps_dev,
-                          const int64_t* hyp_offsets_dev, int64_t n_pairs, int32_t mode, int64_t max_len,
-                          int32_t device, int32_t* out_sdih_dev, int32_t* out_status_dev, void* stream) {
+int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_begin_dev,
+                                const int64_t* ref_end_dev, const uint32_t* hyp_cps_dev,
+                                const int64_t* hyp_begin_dev, const int64_t* hyp_end_dev, int64_t n_pairs,
+                                int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,
+                                int32_t* out_status_dev, void* stream) {
   if (n_pairs < 0 || max_len < 0) return fail(CORAL_EARG, "negative size");
   if (mode < 0 || mode > 2) return fail(CORAL_EARG, "mode must be 0 (tokens), 1 (chars) or 2 (words)");
   if (n_pairs == 0) return CORAL_OK;
-  if (!ref_offsets_dev || !hyp_offsets_dev || !out_sdih_dev || !out_status_dev)
+  if (!ref_begin_dev || !ref_end_dev || !hyp_begin_dev || !hyp_end_dev || !out_sdih_dev || !out_status_dev)
     return fail(CORAL_EARG, "coral_edit_counts: null buffer");
   if (device < 0 || device >= 16) return fail(CORAL_EARG, "device index out of range");
   if (max_len > 8192) return fail(CORAL_ECAP, "strings above 8192 code points are not supported");
@@ -296,8 +299,8 @@ int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offset
     const int64_t need = (n_pairs + WARPS - 1) / WARPS;
     const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * 4);
     edit_counts_kernel<false, 128, WARPS><<<grid, WARPS * 32, 0, st>>>(
-        ref_cps_dev, ref_offsets_dev, hyp_cps_dev, hyp_offsets_dev, n_pairs, mode, out_sdih_dev, out_status_dev,
-        nullptr, 0, 0);
+        ref_cps_dev, ref_begin_dev, ref_end_dev, hyp_cps_dev, hyp_begin_dev, hyp_end_dev, n_pairs, mode,
+        out_sdih_dev, out_status_dev, nullptr, 0, 0);
   } else {
     constexpr int WARPS = 8;
     const int cap = (int)std::max<int64_t>(64, (max_len + 31) / 32 * 32);
@@ -314,11 +317,20 @@ int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offset
       g_edit_work_bytes[device] = bytes;
     }
     edit_counts_kernel<true, 32, WARPS><<<grid, WARPS * 32, 0, st>>>(
-        ref_cps_dev, ref_offsets_dev, hyp_cps_dev, hyp_offsets_dev, n_pairs, mode, out_sdih_dev, out_status_dev,
-        g_edit_work[device], stride, cap);
+        ref_cps_dev, ref_begin_dev, ref_end_dev, hyp_cps_dev, hyp_begin_dev, hyp_end_dev, n_pairs, mode,
+        out_sdih_dev, out_status_dev, g_edit_work[device], stride, cap);
   }
   CORAL_CUDA_OK(cudaGetLastError());
   return CORAL_OK;
+}
+
+int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offsets_dev, const uint32_t* hyp_cps_dev,
+                          const int64_t* hyp_offsets_dev, int64_t n_pairs, int32_t mode, int64_t max_len,
+                          int32_t device, int32_t* out_sdih_dev, int32_t* out_status_dev, void* stream) {
+  if (!ref_offsets_dev || !hyp_offsets_dev) return fail(CORAL_EARG, "coral_edit_counts: null buffer");
+  return coral_edit_counts_spans(ref_cps_dev, ref_offsets_dev, ref_offsets_dev + 1, hyp_cps_dev, hyp_offsets_dev,
+                                 hyp_offsets_dev + 1, n_pairs, mode, max_len, device, out_sdih_dev, out_status_dev,
+                                 stream);
 }
 
 }  // extern "C"

@@ -188,21 +188,10 @@ class BeamSearchDecoderCTC:
         elif not torch.is_tensor(lengths):
             lengths = torch.tensor(list(lengths))
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
-        B, T_max, V = d_logits.shape
-        Tm = max(int(T_max), 1)
         d_order = torch.argsort(d_len, descending=True).to(torch.int32)
-        d_n = torch.zeros(B, dtype=torch.int32, device=dev)
-        d_logit = torch.zeros((B, n_best), dtype=torch.float64, device=dev)
-        d_comb = torch.zeros((B, n_best), dtype=torch.float64, device=dev)
-        d_tok = torch.zeros((B, n_best, Tm), dtype=torch.uint8, device=dev)
-        d_lens = torch.zeros((B, n_best), dtype=torch.int32, device=dev)
-        d_status = torch.zeros(B, dtype=torch.int32, device=dev)
         d_stats = torch.zeros(8, dtype=torch.int64, device=dev) if collect_stats else None
-        _lib.check(_lib.load().coral_ctc_beam_decode(
-            h, d_logits.data_ptr(), d_len.data_ptr(), d_order.data_ptr(), B, int(T_max), V, int(beam_width),
-            float(beam_prune_logp), float(token_min_logp), int(bool(prune_history)), int(input_mode), n_best,
-            d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
-            d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None, _lib.stream_ptr(dev)))
+        d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
+            d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats)
         if not to_host:
             return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats
         out = DecodedBatch(d_n.cpu().numpy(), d_logit.cpu().numpy(), d_comb.cpu().numpy(), d_tok.cpu().numpy(),
@@ -212,6 +201,33 @@ class BeamSearchDecoderCTC:
             bad = np.nonzero(out.status)[0]
             raise _lib.CoralError(int(out.status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
         return out
+
+    def decode_launch(self, d_logits, d_len, d_order, beam_width: int = DEFAULT_BEAM_WIDTH,
+                      beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                      n_best: int = 1, input_mode: int = 0, d_stats=None, events=None):
+        """Queue one batched decode on device-resident inputs (asynchronous). ``events`` =
+        (start, end) ``torch.cuda.Event`` recorded around the library call on the launching stream."""
+        torch = _torch()
+        h = self._handle()
+        dev = d_logits.device
+        B, T_max, V = d_logits.shape
+        Tm = max(int(T_max), 1)
+        d_n = torch.empty(B, dtype=torch.int32, device=dev)
+        d_logit = torch.empty((B, n_best), dtype=torch.float64, device=dev)
+        d_comb = torch.empty((B, n_best), dtype=torch.float64, device=dev)
+        d_tok = torch.zeros((B, n_best, Tm), dtype=torch.uint8, device=dev)
+        d_lens = torch.zeros((B, n_best), dtype=torch.int32, device=dev)
+        d_status = torch.empty(B, dtype=torch.int32, device=dev)
+        if events is not None:
+            events[0].record()
+        _lib.check(_lib.load().coral_ctc_beam_decode(
+            h, d_logits.data_ptr(), d_len.data_ptr(), d_order.data_ptr() if d_order is not None else None, B,
+            int(T_max), V, int(beam_width), float(beam_prune_logp), float(token_min_logp), 0, int(input_mode),
+            int(n_best), d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
+            d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None, _lib.stream_ptr(dev)))
+        if events is not None:
+            events[1].record()
+        return d_n, d_logit, d_comb, d_tok, d_lens, d_status
 
     def tokens_to_text(self, tokens: np.ndarray, lens: np.ndarray) -> list[str]:
         """Alphabet indices -> strings for ``[N, T]`` token rows with ``[N]`` lengths."""

@@ -43,6 +43,24 @@ def edit_counts_device(ref_cps, ref_off, hyp_cps, hyp_off, n_pairs: int, mode: i
     return sdih[:n_pairs], status[:n_pairs]
 
 
+def edit_counts_spans_device(ref_cps, ref_beg, ref_end, hyp_cps, hyp_beg, hyp_end, n_pairs: int, mode: int,
+                             max_len: int, out=None):
+    """Like :func:`edit_counts_device` with explicit ``[begin, end)`` spans per string, e.g.
+    hypotheses still sitting in the padded decoder output (begin = row * pitch)."""
+    torch = _torch()
+    dev = ref_beg.device
+    if out is None:
+        out = (torch.empty((max(n_pairs, 1), 4), dtype=torch.int32, device=dev),
+               torch.empty(max(n_pairs, 1), dtype=torch.int32, device=dev))
+    sdih, status = out
+    _lib.check(_lib.load().coral_edit_counts_spans(
+        ref_cps.data_ptr(), ref_beg.data_ptr(), ref_end.data_ptr(), hyp_cps.data_ptr(), hyp_beg.data_ptr(),
+        hyp_end.data_ptr(), n_pairs, mode, int(max_len),
+        dev.index if dev.index is not None else torch.cuda.current_device(), sdih.data_ptr(), status.data_ptr(),
+        _lib.stream_ptr(dev)))
+    return sdih[:n_pairs], status[:n_pairs]
+
+
 def _upload(strings, dev):
     torch = _torch()
     cps, off = encode_utf32(strings)

@@ -142,6 +142,14 @@ int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offset
                           int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,
                           int32_t* out_status_dev, void* stream);
 
+/* Same, with explicit [begin, end) spans per string (e.g. hypotheses still sitting in the
+ * padded decoder output on the device: begin = row * pitch, end = begin + length). */
+int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_begin_dev,
+                                const int64_t* ref_end_dev, const uint32_t* hyp_cps_dev,
+                                const int64_t* hyp_begin_dev, const int64_t* hyp_end_dev, int64_t n_pairs,
+                                int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,
+                                int32_t* out_status_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

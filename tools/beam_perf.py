@@ -1,0 +1,35 @@
+"""Kernel-level timing of the beam search on a fixed synthetic workload (tuning helper)."""
+import argparse, os, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from coral_b200 import synth
+from coral_b200.decoder import build_ctcdecoder
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--utts", type=int, default=2048)
+ap.add_argument("--beam", type=int, default=100)
+ap.add_argument("--order", type=int, default=5)
+ap.add_argument("--kind", default="peaky")
+ap.add_argument("--shape", default="read_aloud")
+ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--mode", type=int, default=0)
+a = ap.parse_args()
+cache = os.path.join(tempfile.gettempdir(), "coral_b200_cache")
+wl = synth.build_workload(cache, a.utts, order=a.order, kind=a.kind, shape=a.shape, name="eval0")
+dec = build_ctcdecoder(wl.labels, wl.arpa_path)
+dev = torch.device("cuda", 0)
+d_logits = torch.from_numpy(wl.logits).to(dev); d_len = torch.from_numpy(wl.lengths).to(dev)
+d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+for _ in range(2):
+    dec.decode_launch(d_logits, d_len, d_order, beam_width=a.beam, input_mode=a.mode)
+torch.cuda.synchronize()
+ts = []
+for _ in range(a.iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec.decode_launch(d_logits, d_len, d_order, beam_width=a.beam, input_mode=a.mode, events=(e0, e1))
+    torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+frames = int(wl.lengths.sum())
+ms = float(np.median(ts))
+print(f"NT={os.environ.get('CORAL_BEAM_NT','default')} utts={a.utts} beam={a.beam} kind={a.kind}: {ms:.2f} ms  "
+      f"{a.utts/ms*1e3:.0f} utt/s  {ms*1e3/frames*1e3:.1f} ns/frame-amortised  (min {min(ts):.2f})")
