@@ -45,8 +45,8 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
   off[2] = o; o = align16(o + (size_t)ch_size * 8);        // ch_keys
   off[3] = o; o = align16(o + (size_t)ch_size * 4);        // ch_vals
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
-  off[5] = o; o = align16(o + (size_t)outs_cap * sizeof(OutRec));
-  off[6] = o; o = align16(o + (size_t)outs_cap * 2);       // surv
+  off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
+  off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
   return o;
 }
 
@@ -69,21 +69,25 @@ __global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__
     sc.ch_keys = reinterpret_cast<unsigned long long*>(base + off[2]);
     sc.ch_vals = reinterpret_cast<uint32_t*>(base + off[3]);
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
-    sc.outs_g = reinterpret_cast<OutRec*>(base + off[5]);
-    sc.surv_g = reinterpret_cast<uint16_t*>(base + off[6]);
+    sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
+    sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
+    sc.outs_g.order = reinterpret_cast<uint32_t*>(base + off[6]);
+    sc.outs_g.aux = sc.outs_g.order + L.outs_cap;
+    sc.outs_g.child = sc.outs_g.aux + L.outs_cap;
+    sc.outs_g.info = sc.outs_g.child + L.outs_cap;
     sc.node_cap = L.node_cap;
     sc.bnd_cap = L.bnd_cap;
-    sc.ch_mask = L.ch_size - 1;
+    sc.ch_mask_max = L.ch_size - 1;
     sc.outs_cap = L.outs_cap;
   }
-  uint32_t epoch = L.slot_epoch[slot];
+  sc.epoch = L.slot_epoch[slot];
   for (;;) {
     if (threadIdx.x == 0) sm.utt = atomicAdd(L.work, 1);
     group_sync<NT>();
     const int i = sm.utt;
     if (i >= L.B) break;
     const int u = L.order ? L.order[i] : i;
-    sc.epoch = ++epoch;
+    sc.epoch += 1;  // also bumped inside decode() when the child table grows
     UttIO io;
     io.logits = L.logits + (size_t)u * L.P.T_max * L.P.V;
     io.T = L.lengths[u];
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__
     Dec::decode(sm, L.lm, L.P, sc, io);
     group_sync<NT>();
   }
-  if (threadIdx.x == 0) L.slot_epoch[slot] = epoch;
+  if (threadIdx.x == 0) L.slot_epoch[slot] = sc.epoch;
 }
 
 // ---- pyctcdecode's input check: math.isclose(logits.sum(axis=1).mean(), 1) -------------
@@ -169,7 +173,7 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
   uint32_t ch_size = 64;
   while (ch_size < 2 * node_cap) ch_size <<= 1;
-  uint32_t outs_cap = (uint32_t)(bw * (uint64_t)(L.P.V + 1) + 64);
+  uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
   size_t off[7];
   const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
   size_t free_b = 0, total_b = 0;

@@ -135,15 +135,15 @@ struct BndRec {  // LM record of a word boundary (a complete-words text prefix)
   LmState st;
 };
 
-struct alignas(8) OutRec {
-  double comb;
-  double logit;
-  uint32_t order;  // first candidate index in (token-major, beam-minor) order
-  uint32_t aux;    // kind 2: LM word id ; kind 3: boundary record
-  uint32_t child;  // kind 1: representative beam of the live child ; kind 3: node id
-  uint16_t slot;   // hash slot of the source node
-  uint8_t c;       // token
-  uint8_t kf;      // kind (low 2 bits) | lexicon flags << 2
+// Candidates ("outputs") of one frame, struct-of-arrays so that ranking streams over a dense
+// array of 64-bit order-preserving score keys.
+struct OutView {
+  unsigned long long* key;  // ordered_u64(combined score)
+  double* logit;
+  uint32_t* order;  // first candidate index in (token-major, beam-minor) order
+  uint32_t* aux;    // kind 2: LM word id ; kind 3: boundary record
+  uint32_t* child;  // kind 1: representative beam of the live child ; kind 3: node id ; final: text node
+  uint32_t* info;   // source beam (16 bits) | token << 16 | kind/flags << 24
 };
 
 struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after utterance
@@ -152,10 +152,9 @@ struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after 
   unsigned long long* ch_keys;  // epoch << 32 | parent << 8 | tok ; 0 = never used
   uint32_t* ch_vals;
   BndRec* bnd;
-  OutRec* outs_g;       // overflow for frames with more candidates than fit in smem
-  uint16_t* surv_g;
-  uint32_t node_cap, bnd_cap, ch_mask, outs_cap;
-  uint32_t epoch;
+  OutView outs_g;       // overflow for frames with more candidates than fit in smem
+  uint32_t node_cap, bnd_cap, ch_mask_max, outs_cap;
+  uint32_t epoch;       // bumped per utterance and per child-table growth
 };
 
 struct UttIO {
@@ -169,52 +168,62 @@ struct UttIO {
   uint8_t* out_tokens;  // [n_best, T_max]
   int32_t* out_len;     // [n_best]
   int32_t* out_status;  // scalar: 0 ok, -4 capacity
-  unsigned long long* stats;  // optional [8]: extensions, LM scorings, n-gram probes, frames, lexicon probes
+  // optional [8]: extensions, LM scorings, n-gram probes, frames, lexicon probes, trie nodes,
+  // LM boundary records, child-table growths
+  unsigned long long* stats;
 };
+
+constexpr uint32_t kChInit = 4096;  // initial child-table size per utterance (grows x4)
 
 template <int BW, int OUTC>
 struct GroupShared {
-  static constexpr int HS = 2 * BW;
+  static constexpr int HS = BW <= 32 ? 64 : (BW <= 64 ? 128 : (BW <= 128 ? 256 : (BW <= 256 ? 512 : 1024)));
   // beams, double buffered
   double logit[2][BW];
   double lm_raw[2][BW];
   unsigned long long whash[2][BW];
   uint32_t node[2][BW];
   uint32_t parent[2][BW];
+  uint32_t gparent[2][BW];
   uint32_t bnd[2][BW];
   uint32_t wid[2][BW];
-  uint32_t meta[2][BW];  // tok | lc << 8 | flags << 16 | wlen << 20
+  uint32_t meta[2][BW];  // tok | lc << 8 | flags << 16 | parent's tok << 24
+  uint16_t wlen[2][BW];
   // live-node hash
   unsigned long long hkey[HS];
   uint16_t sb0[HS], sb1[HS];
   uint16_t ne_slot[BW];
-  uint16_t beam_slot[BW];
-  uint8_t claimed[HS];
-  // candidates of this frame
-  OutRec outs[OUTC];
-  uint16_t surv[OUTC];
-  uint32_t hist[256];
+  // candidates of this frame (also reused as the 256-bin histogram of the overflow path)
+  unsigned long long o_key[OUTC];
+  double o_logit[OUTC];
+  uint32_t o_order[OUTC];
+  uint32_t o_aux[OUTC];
+  uint32_t o_child[OUTC];
+  uint32_t o_info[OUTC];
   // staged frames
   float lp[kChunk][kVMax];
   uint8_t kept[kChunk][kVMax];
   uint8_t nkept[kChunk];
-  uint8_t krank[kVMax];
-  // scalars
-  unsigned long long gmax;
+  // scalars; the per-frame counters are double-buffered by frame parity so that the next
+  // frame's copy can be cleared without an extra barrier
+  unsigned long long gmax[2];
   unsigned long long sel_prefix, sel_mask;
-  uint32_t nb, nN, n_out, S, S2;
-  uint32_t node_count, bnd_count;
-  uint32_t sel_need, sel_eq;
-  int32_t cur, status, utt;
+  uint32_t nN[2], n_out[2], S[2];
+  uint32_t node_count, bnd_count, ch_mask;
+  uint32_t sel_need, sel_eq, sel_cut, sel_n;
+  uint32_t gsum[16];
+  int32_t status, utt;
 };
 
-CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags, uint32_t wlen) {
-  return tok | (lc << 8) | (flags << 16) | ((wlen > 4095u ? 4095u : wlen) << 20);
+CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags, uint32_t ptok) {
+  return tok | (lc << 8) | (flags << 16) | (ptok << 24);
 }
 CORAL_HD uint32_t meta_tok(uint32_t m) { return m & 0xFFu; }
 CORAL_HD uint32_t meta_lc(uint32_t m) { return (m >> 8) & 0xFFu; }
-CORAL_HD uint32_t meta_flags(uint32_t m) { return (m >> 16) & 0xFu; }
-CORAL_HD uint32_t meta_wlen(uint32_t m) { return m >> 20; }
+CORAL_HD uint32_t meta_flags(uint32_t m) { return (m >> 16) & 0xFFu; }
+CORAL_HD uint32_t meta_ptok(uint32_t m) { return m >> 24; }
+constexpr uint32_t kLcNone = 0xFFu;   // last_char None (start of utterance)
+constexpr uint32_t kLcBlank = 0xFEu;  // last_char "" (blank)
 
 CORAL_HD unsigned long long node_key(uint32_t parent, uint32_t tok) {
   // root is (kNoNode, kNoTok); +1 keeps every key non-zero
@@ -231,7 +240,7 @@ CORAL_HD double partial_score(const DecodeParams& P, uint32_t wlen, uint32_t fla
 
 // pyctcdecode LanguageModel.score: alpha * log10-score * ln10 + beta
 CORAL_DEV double lm_word_score(const LmView& lm, const DecodeParams& P, const LmState& in, uint32_t wid,
-                              bool oov, bool is_last, LmState& out, unsigned long long* stats) {
+                               bool oov, bool is_last, LmState& out, unsigned long long* stats) {
   int np = 0;
   double x = (double)lm_base_score(lm, in, wid, out, &np);
   if (oov) x = d_add(x, P.unk_score_offset);
@@ -264,54 +273,84 @@ struct BeamDecoder {
       i = (i + 1) & (HS - 1);
     }
   }
-  static CORAL_DEV int h_insert(Sm& sm, unsigned long long key) {
+  // returns the slot; `created` tells the caller it is the one that inserted the key
+  static CORAL_DEV int h_insert(Sm& sm, unsigned long long key, bool& created) {
     uint32_t i = (uint32_t)mix64(key) & (HS - 1);
     for (;;) {
       const unsigned long long k = atom_cas_u64(&sm.hkey[i], 0ULL, key);
-      if (k == 0 || k == key) return (int)i;
+      if (k == 0) { created = true; return (int)i; }
+      if (k == key) { created = false; return (int)i; }
       i = (i + 1) & (HS - 1);
     }
   }
 
   // ---- per-utterance trie child table (HBM) ------------------------------------------
-  // Returns the node id of (parent, tok), creating it (with info word `info`) if absent.
+  // Keys carry the slot's epoch, so entries of earlier utterances (or of the table before
+  // it grew) read as empty and nothing is ever cleared.
+  static CORAL_DEV unsigned long long ch_key(const SlotScratch& sc, uint32_t parent, uint32_t tok) {
+    return ((unsigned long long)sc.epoch << 32) | ((unsigned long long)(parent & 0xFFFFFFu) << 8) | tok;
+  }
+  static CORAL_DEV void ch_put(Sm& sm, const SlotScratch& sc, unsigned long long key, uint32_t id) {
+    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
+    for (;;) {
+      const unsigned long long k = sc.ch_keys[i];
+      if ((k >> 32) != sc.epoch) {
+        if (atom_cas_u64(&sc.ch_keys[i], k, key) == k) { sc.ch_vals[i] = id; return; }
+        continue;  // lost the slot to another lane: look at it again
+      }
+      i = (i + 1) & sm.ch_mask;
+    }
+  }
+  // Returns the node id of (parent, tok), creating it if absent.
   static CORAL_DEV uint32_t trie_get_or_add(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok,
-                                            uint32_t bnd, bool& created) {
-    const unsigned long long tag = (unsigned long long)sc.epoch << 32;
-    const unsigned long long key = tag | ((unsigned long long)(parent & 0xFFFFFFu) << 8) | tok;
-    uint32_t i = (uint32_t)mix64(key) & sc.ch_mask;
-    created = false;
+                                            uint32_t bnd) {
+    const unsigned long long key = ch_key(sc, parent, tok);
+    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
     uint32_t id = kNoNode;
     for (;;) {
-      unsigned long long k = sc.ch_keys[i];
+      const unsigned long long k = sc.ch_keys[i];
       if (k == key) return sc.ch_vals[i];
-      if ((k >> 32) != sc.epoch) {  // empty or left over from an earlier utterance
+      if ((k >> 32) != sc.epoch) {  // empty or stale
         if (id == kNoNode) id = atom_add(&sm.node_count, 1u);
         if (id >= sc.node_cap) { sm.status = -4; return 0; }
-        const unsigned long long old = atom_cas_u64(&sc.ch_keys[i], k, key);
-        if (old == k) {
+        if (atom_cas_u64(&sc.ch_keys[i], k, key) == k) {
           sc.ch_vals[i] = id;
           sc.node_parent[id] = parent;
           sc.node_info[id] = tok | (bnd << 8);
-          created = true;
           return id;
         }
-        // lost the slot to another lane (a different key: keys are unique per frame)
-        continue;
+        continue;  // lost the slot to another lane (a different key: keys are unique per frame)
       }
-      i = (i + 1) & sc.ch_mask;
+      i = (i + 1) & sm.ch_mask;
     }
   }
-  static CORAL_DEV bool trie_find(const SlotScratch& sc, uint32_t parent, uint32_t tok, uint32_t& id) {
-    const unsigned long long tag = (unsigned long long)sc.epoch << 32;
-    const unsigned long long key = tag | ((unsigned long long)(parent & 0xFFFFFFu) << 8) | tok;
-    uint32_t i = (uint32_t)mix64(key) & sc.ch_mask;
+  static CORAL_DEV bool trie_find(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok, uint32_t& id) {
+    const unsigned long long key = ch_key(sc, parent, tok);
+    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
     for (;;) {
       const unsigned long long k = sc.ch_keys[i];
       if (k == key) { id = sc.ch_vals[i]; return true; }
       if ((k >> 32) != sc.epoch) return false;
-      i = (i + 1) & sc.ch_mask;
+      i = (i + 1) & sm.ch_mask;
     }
+  }
+  // Keep the child table at most half full: grow x4 (new epoch, re-insert every node).
+  static CORAL_DEV void trie_maybe_grow(Sm& sm, SlotScratch& sc, const DecodeParams& P, const UttIO& io) {
+    const uint32_t need = (sm.node_count + 2u * (uint32_t)P.beam_width + 2u) * 2u;
+    if (need <= sm.ch_mask + 1u || sm.ch_mask >= sc.ch_mask_max) return;  // uniform: read after a barrier
+    uint32_t size = sm.ch_mask + 1u;
+    while (size < need && size - 1u < sc.ch_mask_max) size <<= 2;
+    if (size - 1u > sc.ch_mask_max) size = sc.ch_mask_max + 1u;
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) { if (lane == 0) { sm.ch_mask = size - 1u; if (io.stats) atom_add(&io.stats[7], 1ULL); } }
+    sc.epoch += 1;
+    CORAL_GSYNC(NT);
+    const uint32_t n = sm.node_count;
+    CORAL_LANES(NT) {
+      for (uint32_t id = 1 + lane; id < n; id += NT)
+        ch_put(sm, sc, ch_key(sc, sc.node_parent[id], sc.node_info[id] & 0xFFu), id);
+    }
+    CORAL_GSYNC(NT);
   }
 
   // ---- frame staging: log-softmax in float32 the way numpy evaluates it ---------------
@@ -377,8 +416,7 @@ struct BeamDecoder {
   // Sequential log-sum-exp of (logit[b] + p) over up to four member beams in ascending
   // beam index (= the reference's candidate order within one token). Returns min index.
   static CORAL_DEV uint32_t merge_members(Sm& sm, int cur, uint32_t m[4], int n, double p, double& score) {
-    // insertion sort of <= 4 indices
-    for (int a = 1; a < n; ++a) {
+    for (int a = 1; a < n; ++a) {  // insertion sort of <= 4 indices
       uint32_t x = m[a];
       int b = a - 1;
       while (b >= 0 && m[b] > x) { m[b + 1] = m[b]; --b; }
@@ -389,437 +427,425 @@ struct BeamDecoder {
     return m[0];
   }
 
-  // ---- phase 1: hash the live nodes ----------------------------------------------------
-  static CORAL_DEV void build_node_hash(Sm& sm) {
-    const int cur = sm.cur;
+  static CORAL_DEV OutView smem_outs(Sm& sm) {
+    OutView o;
+    o.key = sm.o_key; o.logit = sm.o_logit; o.order = sm.o_order; o.aux = sm.o_aux; o.child = sm.o_child;
+    o.info = sm.o_info;
+    return o;
+  }
+  static CORAL_DEV void emit(Sm& sm, const OutView& o, int q, double comb, double logit, uint32_t order, uint32_t aux,
+                             uint32_t child, uint32_t rb, uint32_t c, uint32_t kf, unsigned long long& lmax) {
+    const uint32_t at = atom_add(&sm.n_out[q], 1u);
+    const unsigned long long k = ordered_u64(comb);
+    o.key[at] = k;
+    o.logit[at] = logit;
+    o.order[at] = order;
+    o.aux[at] = aux;
+    o.child[at] = child;
+    o.info[at] = rb | (c << 16) | (kf << 24);
+    lmax = k > lmax ? k : lmax;
+  }
+
+  // ---- phase 1: hash the live nodes of the current beam list -----------------------------
+  // The hash was cleared during the previous frame's phase 3. The lane whose CAS inserts a
+  // node registers it in the node list; every beam records itself in its node's slot.
+  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb) {
     CORAL_LANES(NT) {
-      for (int i = lane; i < HS; i += NT) { sm.hkey[i] = 0; sm.sb0[i] = kNone16; sm.sb1[i] = kNone16; sm.claimed[i] = 0; }
-      if (lane == 0) { sm.nN = 0; sm.n_out = 0; sm.S = 0; sm.S2 = 0; sm.gmax = 0; }
-    }
-    CORAL_GSYNC(NT);
-    const uint32_t nb = sm.nb;
-    CORAL_LANES(NT) {
+      if (lane == 0) { sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0; }
       for (uint32_t b = lane; b < nb; b += NT) {
         const uint32_t mt = sm.meta[cur][b];
-        const int s = h_insert(sm, node_key(sm.parent[cur][b], meta_tok(mt)));
-        sm.beam_slot[b] = (uint16_t)s;
-      }
-    }
-    CORAL_GSYNC(NT);
-    CORAL_LANES(NT) {
-      for (uint32_t b = lane; b < nb; b += NT) {
-        const int s = sm.beam_slot[b];
-        if (meta_lc(sm.meta[cur][b]) == (uint32_t)0xFE) sm.sb0[s] = (uint16_t)b;  // 0xFE = blank marker
-        else sm.sb1[s] = (uint16_t)b;
-      }
-    }
-    CORAL_GSYNC(NT);
-    CORAL_LANES(NT) {
-      for (uint32_t b = lane; b < nb; b += NT) {
-        const int s = sm.beam_slot[b];
-        const uint32_t a = sm.sb0[s], c = sm.sb1[s];
-        const uint32_t first = a < c ? a : c;  // kNone16 is larger than any index
-        if (first == b) { const uint32_t j = atom_add(&sm.nN, 1u); sm.ne_slot[j] = (uint16_t)s; }
+        bool created;
+        const int s = h_insert(sm, node_key(sm.parent[cur][b], meta_tok(mt)), created);
+        if (created) sm.ne_slot[atom_add(&sm.nN[q], 1u)] = (uint16_t)s;
+        if (meta_lc(mt) == kLcBlank) sm.sb0[s] = (uint16_t)b; else sm.sb1[s] = (uint16_t)b;
       }
     }
     CORAL_GSYNC(NT);
   }
 
-  // ---- one frame ------------------------------------------------------------------------
-  static CORAL_DEV void frame_step(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
-                                   const UttIO& io, int f) {
-    build_node_hash(sm);
-    const int cur = sm.cur;
-    const int K = sm.nkept[f];
-    const uint32_t nb = sm.nb, nN = sm.nN;
-    const uint32_t n_slots = nN * (uint32_t)K + nN;
-    OutRec* outs = n_slots <= (uint32_t)OUTC ? sm.outs : sc.outs_g;
-    uint16_t* surv = n_slots <= (uint32_t)OUTC ? sm.surv : sc.surv_g;
-    if (n_slots > sc.outs_cap && n_slots > (uint32_t)OUTC) { CORAL_LANES(NT) { if (lane == 0) sm.status = -4; } CORAL_GSYNC(NT); return; }
-    CORAL_LANES(NT) {
-      for (int v = lane; v < P.V; v += NT) sm.krank[v] = 0xFF;
-    }
-    CORAL_GSYNC(NT);
-    CORAL_LANES(NT) {
-      for (int k = lane; k < K; k += NT) sm.krank[sm.kept[f][k]] = (uint8_t)k;
-      if (lane == 0 && io.stats) { atom_add(&io.stats[0], (unsigned long long)K * nb); atom_add(&io.stats[3], 1ULL); }
-    }
-    CORAL_GSYNC(NT);
+  static CORAL_DEV void clear_hash(Sm& sm, int lane) {
+    for (int i = lane; i < HS; i += NT) { sm.hkey[i] = 0; sm.sb0[i] = kNone16; sm.sb1[i] = kNone16; }
+  }
 
-    // -- phase 2a: every (live node, kept token) --------------------------------------
+  // ---- phase 2: every (live node, kept token), plus repeats of nodes whose parent is dead ---
+  static CORAL_DEV void expand(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                               const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs) {
+    const int K = sm.nkept[f];
+    const uint32_t nN = sm.nN[q];
     CORAL_LANES(NT) {
+      if (lane == 0 && io.stats) { atom_add(&io.stats[0], (unsigned long long)K * nb); atom_add(&io.stats[3], 1ULL); }
       unsigned long long lmax = 0;
-      for (uint32_t i = lane; i < nN * (uint32_t)K; i += NT) {
-        const uint32_t j = i / K, k = i % K;
+      const uint32_t n1 = nN * (uint32_t)K;
+      for (uint32_t i = lane; i < n1 + nN; i += NT) {
+        const bool fam2 = i >= n1;
+        const uint32_t j = fam2 ? i - n1 : i / K;
         const int s = sm.ne_slot[j];
-        const uint32_t c = sm.kept[f][k];
-        const double p = (double)sm.lp[f][c];
         const uint32_t rb = rep_beam(sm, s);
         const uint32_t mt = sm.meta[cur][rb];
-        const uint32_t tok_m = meta_tok(mt), wlen_m = meta_wlen(mt), fl_m = meta_flags(mt);
+        const uint32_t tok_m = meta_tok(mt), fl_m = meta_flags(mt), wlen_m = sm.wlen[cur][rb];
         const uint32_t b0 = sm.sb0[s], b1 = sm.sb1[s];
-        OutRec o;
-        o.slot = (uint16_t)s;
-        o.c = (uint8_t)c;
-        o.aux = 0;
-        o.child = 0;
         uint32_t mem[4];
         int nm = 0;
-        bool valid = true;
+        double logit;
+        if (fam2) {
+          // repeat of the node's own last token (or a space on a closed word): the text does
+          // not change. If the parent node is live, its (parent, c) item gathers these beams.
+          const uint32_t c = tok_m == kNoTok ? (uint32_t)P.space_id : tok_m;
+          if (tok_m != kNoTok && h_find(sm, node_key(sm.gparent[cur][rb], meta_ptok(mt))) >= 0) continue;
+          int k = -1;
+          for (int kk = 0; kk < K; ++kk) if (sm.kept[f][kk] == c) k = kk;
+          if (k < 0) continue;
+          if (b1 != kNone16) mem[nm++] = b1;  // last_char == c (None or space at the root)
+          if ((int)c == P.space_id && b0 != kNone16) mem[nm++] = b0;
+          if (nm == 0) continue;
+          const uint32_t first = merge_members(sm, cur, mem, nm, (double)sm.lp[f][c], logit);
+          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+               (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax);
+          continue;
+        }
+        const uint32_t k = i % K;
+        const uint32_t c = sm.kept[f][k];
+        const double p = (double)sm.lp[f][c];
         if ((int)c == P.blank_id) {
           if (b0 != kNone16) mem[nm++] = b0;
           if (b1 != kNone16) mem[nm++] = b1;
-          const uint32_t first = merge_members(sm, cur, mem, nm, p, o.logit);
-          o.order = k * nb + first;
-          o.kf = 0;
-          o.comb = d_add(o.logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m)));
-        } else if ((int)c == P.space_id && wlen_m == 0) {
-          valid = false;  // a space after a closed word / at the start never extends
-        } else {
-          if (b0 != kNone16) mem[nm++] = b0;
-          if (b1 != kNone16 && tok_m != c) mem[nm++] = b1;
-          const int cs = h_find(sm, node_key(sm.node[cur][rb], c));
-          if (cs >= 0) {
-            sm.claimed[cs] = 1;
-            if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
-            if ((int)c == P.space_id && sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
-          }
-          if (nm == 0) {
-            valid = false;
-          } else {
-            const uint32_t first = merge_members(sm, cur, mem, nm, p, o.logit);
-            o.order = k * nb + first;
-            if (cs >= 0) {
-              const uint32_t crb = rep_beam(sm, cs);
-              const uint32_t cmt = sm.meta[cur][crb];
-              o.kf = 1;
-              o.child = crb;
-              o.comb = d_add(o.logit, d_add(sm.lm_raw[cur][crb], partial_score(P, meta_wlen(cmt), meta_flags(cmt))));
-            } else if ((int)c == P.space_id) {
-              // a word closes: the boundary node is materialised at once (it carries the
-              // LM record, like pyctcdecode's cached_lm_scores entry for the new text)
-              uint32_t nid = 0, bnd_new = 0;
-              double raw_new = sm.lm_raw[cur][rb];
-              bool have = false;
-              if (trie_find(sc, sm.node[cur][rb], c, nid)) {
-                bnd_new = sc.node_info[nid] >> 8;
-                if (lm.present) raw_new = sc.bnd[bnd_new].lm_raw;
-                have = true;
-              }
-              if (!have) {
-                if (lm.present) {
-                  bnd_new = atom_add(&sm.bnd_count, 1u);
-                  if (bnd_new >= sc.bnd_cap) { sm.status = -4; bnd_new = 0; }
-                  const bool in_lm = (fl_m & kInLm) != 0;
-                  const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
-                  BndRec nr;
-                  const double sc_w = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u,
-                                                    oov, false, nr.st, io.stats);
-                  nr.lm_raw = d_add(sm.lm_raw[cur][rb], sc_w);
-                  raw_new = nr.lm_raw;
-                  sc.bnd[bnd_new] = nr;
-                }
-                bool created;
-                nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, bnd_new, created);
-              }
-              o.kf = 3;
-              o.child = nid;
-              o.aux = bnd_new;
-              o.comb = d_add(o.logit, d_add(raw_new, 0.0));
-            } else {
-              // a letter extends the partial word: roll the word hash, probe the lexicon
-              uint32_t nfl = fl_m & kDead ? (kDead | kOovPartial) : 0u;
-              uint32_t nwid = 0;
-              if (lm.present) {
-                if (!(fl_m & kDead)) {
-                  unsigned long long h = sm.whash[cur][rb];
-                  for (int q = 0; q < P.label_ncp[c]; ++q) h = word_hash_push(h, P.label_cps[c][q]);
-                  uint32_t lw, lf;
-                  if (io.stats) atom_add(&io.stats[4], 1ULL);
-                  if (lex_find(lm, h, lw, lf)) {
-                    nfl = ((lf & kLexPrefixOfUnigram) ? 0u : kOovPartial) | ((lf & kLexInUnigrams) ? kInUni : 0u) |
-                          ((lf & kLexInLm) ? kInLm : 0u);
-                    nwid = lw;
-                  } else {
-                    nfl = kDead | kOovPartial;
-                  }
-                }
-              } else {
-                nfl = 0;
-              }
-              o.kf = (uint8_t)(2u | (nfl << 2));
-              o.aux = nwid;
-              const double ps = lm.present ? partial_score(P, wlen_m + P.label_ncp[c], nfl) : 0.0;
-              o.comb = d_add(o.logit, d_add(sm.lm_raw[cur][rb], ps));
-            }
-          }
-        }
-        if (valid) {
-          const uint32_t at = atom_add(&sm.n_out, 1u);
-          outs[at] = o;
-          const unsigned long long ok = ordered_u64(o.comb);
-          lmax = ok > lmax ? ok : lmax;
-        }
-      }
-      if (lmax) atom_max_u64(&sm.gmax, lmax);
-    }
-    CORAL_GSYNC(NT);
-    // -- phase 2b: repeats / closing spaces of nodes whose parent is not live -----------
-    CORAL_LANES(NT) {
-      unsigned long long lmax = 0;
-      for (uint32_t j = lane; j < nN; j += NT) {
-        const int s = sm.ne_slot[j];
-        if (sm.claimed[s]) continue;
-        const uint32_t rb = rep_beam(sm, s);
-        const uint32_t mt = sm.meta[cur][rb];
-        const uint32_t tok_m = meta_tok(mt);
-        const uint32_t c = tok_m == kNoTok ? (uint32_t)P.space_id : tok_m;
-        const uint32_t k = sm.krank[c];
-        if (k == 0xFF) continue;
-        uint32_t mem[4];
-        int nm = 0;
-        const uint32_t b0 = sm.sb0[s], b1 = sm.sb1[s];
-        if (b1 != kNone16) mem[nm++] = b1;  // last_char == c (or None/space at the root)
-        if ((int)c == P.space_id && b0 != kNone16) mem[nm++] = b0;
-        if (nm == 0) continue;
-        OutRec o;
-        o.slot = (uint16_t)s;
-        o.c = (uint8_t)c;
-        o.aux = 0;
-        o.child = 0;
-        o.kf = 0;
-        const uint32_t first = merge_members(sm, cur, mem, nm, (double)sm.lp[f][c], o.logit);
-        o.order = k * nb + first;
-        o.comb = d_add(o.logit, d_add(sm.lm_raw[cur][rb], partial_score(P, meta_wlen(mt), meta_flags(mt))));
-        const uint32_t at = atom_add(&sm.n_out, 1u);
-        outs[at] = o;
-        const unsigned long long ok = ordered_u64(o.comb);
-        lmax = ok > lmax ? ok : lmax;
-      }
-      if (lmax) atom_max_u64(&sm.gmax, lmax);
-    }
-    CORAL_GSYNC(NT);
-    select_and_commit(sm, lm, P, sc, outs, surv, false);
-  }
-
-  // ---- prune, trim to beam_width, rank, write the next beam list ------------------------
-  static CORAL_DEV void select_and_commit(Sm& sm, const LmView& lm, const DecodeParams& P,
-                                          const SlotScratch& sc, OutRec* outs, uint16_t* surv, bool final_pass) {
-    const int cur = sm.cur, nxt = cur ^ 1;
-    const uint32_t n_out = sm.n_out;
-    // max_score + beam_prune_logp, compared in float64
-    double maxs;
-    {
-      unsigned long long u = sm.gmax;
-      u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
-      union { double d; unsigned long long u; } c;
-      c.u = u;
-      maxs = c.d;
-    }
-    const double thr = d_add(maxs, P.beam_prune_logp);
-    CORAL_LANES(NT) {
-      for (uint32_t i = lane; i < n_out; i += NT)
-        if (outs[i].comb >= thr) surv[atom_add(&sm.S, 1u)] = (uint16_t)i;
-    }
-    CORAL_GSYNC(NT);
-    uint32_t S = sm.S;
-    if (S > (uint32_t)P.beam_width) {
-      // radix select of the beam_width best by (score desc, first-candidate index asc)
-      CORAL_LANES(NT) { if (lane == 0) { sm.sel_prefix = 0; sm.sel_mask = 0; sm.sel_need = (uint32_t)P.beam_width; } }
-      CORAL_GSYNC(NT);
-      for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        CORAL_LANES(NT) { for (int i = lane; i < 256; i += NT) sm.hist[i] = 0; }
-        CORAL_GSYNC(NT);
-        const unsigned long long pre = sm.sel_prefix, msk = sm.sel_mask;
-        CORAL_LANES(NT) {
-          for (uint32_t i = lane; i < S; i += NT) {
-            const unsigned long long k = ordered_u64(outs[surv[i]].comb);
-            if ((k & msk) == pre) atom_add(&sm.hist[(k >> shift) & 255], 1u);
-          }
-        }
-        CORAL_GSYNC(NT);
-        CORAL_LANES(NT) {
-          if (lane == 0) {
-            uint32_t cum = 0, need = sm.sel_need;
-            int d = 255;
-            for (; d > 0; --d) { if (cum + sm.hist[d] >= need) break; cum += sm.hist[d]; }
-            sm.sel_need = need - cum;
-            sm.sel_eq = sm.hist[d];
-            sm.sel_prefix = pre | ((unsigned long long)d << shift);
-            sm.sel_mask = msk | (255ULL << shift);
-          }
-        }
-        CORAL_GSYNC(NT);
-      }
-      const unsigned long long kth = sm.sel_prefix;
-      // ties at the cut: keep the sel_need smallest candidate indices
-      uint32_t ord_cut = 0xFFFFFFFFu;
-      if (sm.sel_eq != sm.sel_need) {
-        CORAL_LANES(NT) {
-          if (lane == 0) {
-            // rare: select by repeated minimum
-            uint32_t last = 0; bool first = true; uint32_t cut = 0;
-            for (uint32_t r = 0; r < sm.sel_need; ++r) {
-              uint32_t best = 0xFFFFFFFFu;
-              for (uint32_t i = 0; i < S; ++i) {
-                const OutRec& o = outs[surv[i]];
-                if (ordered_u64(o.comb) == kth && (first || o.order > last) && o.order < best) best = o.order;
-              }
-              last = best; first = false; cut = best;
-            }
-            sm.sel_need = cut;  // reuse as the order cut
-          }
-        }
-        CORAL_GSYNC(NT);
-        ord_cut = sm.sel_need;
-      }
-      // losers are marked kNone16 in place; the ranking below skips them
-      CORAL_LANES(NT) {
-        for (uint32_t i = lane; i < S; i += NT) {
-          const OutRec& o = outs[surv[i]];
-          const unsigned long long k = ordered_u64(o.comb);
-          if (!(k > kth || (k == kth && o.order <= ord_cut))) surv[i] = (uint16_t)kNone16;
-        }
-      }
-      CORAL_GSYNC(NT);
-    }
-    // rank every survivor and write it at its position in the other beam buffer
-    CORAL_LANES(NT) {
-      for (uint32_t i = lane; i < S; i += NT) {
-        const uint32_t oi = surv[i];
-        if (oi == kNone16) continue;
-        const OutRec o = outs[oi];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < S; ++j) {
-          const uint32_t oj = surv[j];
-          if (oj == kNone16) continue;
-          const double cj = outs[oj].comb;
-          r += (cj > o.comb) || (cj == o.comb && outs[oj].order < o.order);
-        }
-        if (final_pass) {
-          sm.logit[nxt][r] = o.logit;
-          sm.lm_raw[nxt][r] = o.comb;   // final: combined score travels in lm_raw
-          sm.node[nxt][r] = o.child;    // final: text node
+          const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
+          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+               k * nb + first, 0u, 0u, rb, c, 0u, lmax);
           continue;
         }
-        const int s = o.slot;
-        const uint32_t rb = rep_beam(sm, s);
-        const uint32_t kind = o.kf & 3u;
-        const uint32_t c = o.c;
-        const uint32_t lc = (int)c == P.blank_id ? 0xFEu : c;
+        if ((int)c == P.space_id && wlen_m == 0) continue;  // a space after a closed word never extends
+        if (b0 != kNone16) mem[nm++] = b0;
+        if (b1 != kNone16 && tok_m != c) mem[nm++] = b1;
+        const int cs = h_find(sm, node_key(sm.node[cur][rb], c));
+        if (cs >= 0) {
+          if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
+          if ((int)c == P.space_id && sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
+        }
+        if (nm == 0) continue;
+        const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
+        const uint32_t order = k * nb + first;
+        if (cs >= 0) {
+          const uint32_t crb = rep_beam(sm, cs);
+          emit(sm, outs, q,
+               d_add(logit, d_add(sm.lm_raw[cur][crb],
+                                  partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])))),
+               logit, order, 0u, crb, rb, c, 1u, lmax);
+        } else if ((int)c == P.space_id) {
+          // a word closes: the boundary node is materialised at once (it carries the LM
+          // record, like pyctcdecode's cached_lm_scores entry for the new text)
+          uint32_t nid = 0, bnd_new = 0;
+          double raw_new = sm.lm_raw[cur][rb];
+          if (trie_find(sm, sc, sm.node[cur][rb], c, nid)) {
+            bnd_new = sc.node_info[nid] >> 8;
+            if (lm.present) raw_new = sc.bnd[bnd_new].lm_raw;
+          } else {
+            if (lm.present) {
+              bnd_new = atom_add(&sm.bnd_count, 1u);
+              if (bnd_new >= sc.bnd_cap) { sm.status = -4; bnd_new = 0; }
+              const bool in_lm = (fl_m & kInLm) != 0;
+              const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
+              BndRec nr;
+              const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u, oov,
+                                              false, nr.st, io.stats);
+              nr.lm_raw = d_add(sm.lm_raw[cur][rb], sw);
+              raw_new = nr.lm_raw;
+              sc.bnd[bnd_new] = nr;
+            }
+            nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, bnd_new);
+          }
+          emit(sm, outs, q, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, nid, rb, c, 3u, lmax);
+        } else {
+          // a letter extends the partial word: roll the word hash, probe the lexicon
+          uint32_t nfl = 0, nwid = 0;
+          double ps = 0.0;
+          if (lm.present) {
+            if (fl_m & kDead) {
+              nfl = kDead | kOovPartial;
+            } else {
+              unsigned long long h = sm.whash[cur][rb];
+              for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
+              uint32_t lw, lf;
+              if (io.stats) atom_add(&io.stats[4], 1ULL);
+              if (lex_find(lm, h, lw, lf)) {
+                nfl = ((lf & kLexPrefixOfUnigram) ? 0u : kOovPartial) | ((lf & kLexInUnigrams) ? kInUni : 0u) |
+                      ((lf & kLexInLm) ? kInLm : 0u);
+                nwid = lw;
+              } else {
+                nfl = kDead | kOovPartial;
+              }
+            }
+            ps = partial_score(P, wlen_m + P.label_ncp[c], nfl);
+          }
+          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
+               2u | (nfl << 2), lmax);
+        }
+      }
+      if (lmax) atom_max_u64(&sm.gmax[q], lmax);
+    }
+    CORAL_GSYNC(NT);
+  }
+
+  // ---- overflow path: more candidates than the shared-memory arrays hold ------------------
+  // Radix-select the beam_width best keys in HBM, then pull the winners into shared memory
+  // so that phase 3 ranks them exactly like the common case. `thr` = prune threshold key.
+  static CORAL_DEV void select_overflow(Sm& sm, const DecodeParams& P, const OutView& g, int q,
+                                        unsigned long long thr) {
+    const uint32_t n = sm.n_out[q];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sm.o_key);  // 256 bins; o_key is unused until the pull
+    CORAL_LANES(NT) { if (lane == 0) { sm.sel_prefix = 0; sm.sel_mask = 0; sm.sel_need = (uint32_t)P.beam_width; sm.sel_n = 0; } }
+    CORAL_GSYNC(NT);
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      CORAL_LANES(NT) { for (int i = lane; i < 256; i += NT) hist[i] = 0; }
+      CORAL_GSYNC(NT);
+      const unsigned long long pre = sm.sel_prefix, msk = sm.sel_mask;
+      CORAL_LANES(NT) {
+        for (uint32_t i = lane; i < n; i += NT) {
+          const unsigned long long k = g.key[i];
+          if (k >= thr && (k & msk) == pre) atom_add(&hist[(k >> shift) & 255], 1u);
+        }
+      }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        for (int gq = lane; gq < 16; gq += NT) {
+          uint32_t t = 0;
+          for (int d = 0; d < 16; ++d) t += hist[gq * 16 + d];
+          sm.gsum[gq] = t;
+        }
+      }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        if (lane == 0) {
+          uint32_t cum = 0, need = sm.sel_need;
+          int gq = 15;
+          for (; gq > 0; --gq) { if (cum + sm.gsum[gq] >= need) break; cum += sm.gsum[gq]; }
+          int d = gq * 16 + 15;
+          for (; d > gq * 16; --d) { if (cum + hist[d] >= need) break; cum += hist[d]; }
+          sm.sel_need = need - cum;
+          sm.sel_eq = hist[d];
+          sm.sel_prefix = pre | ((unsigned long long)d << shift);
+          sm.sel_mask = msk | (255ULL << shift);
+        }
+      }
+      CORAL_GSYNC(NT);
+    }
+    const unsigned long long kth = sm.sel_prefix;
+    // fewer than beam_width survivors in total: everything >= thr is taken (kth <= thr then)
+    uint32_t ord_cut = 0xFFFFFFFFu;
+    if (sm.sel_eq > sm.sel_need) {  // ties at the cut: keep the sel_need smallest candidate indices
+      CORAL_LANES(NT) {
+        if (lane == 0) {
+          uint32_t last = 0, cut = 0;
+          bool first = true;
+          for (uint32_t r = 0; r < sm.sel_need; ++r) {
+            uint32_t best = 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < n; ++i)
+              if (g.key[i] == kth && (first || g.order[i] > last) && g.order[i] < best) best = g.order[i];
+            last = best;
+            first = false;
+            cut = best;
+          }
+          sm.sel_cut = cut;
+        }
+      }
+      CORAL_GSYNC(NT);
+      ord_cut = sm.sel_cut;
+    }
+    CORAL_LANES(NT) {
+      for (uint32_t i = lane; i < n; i += NT) {
+        const unsigned long long k = g.key[i];
+        if (k < thr) continue;
+        if (k > kth || (k == kth && g.order[i] <= ord_cut)) {
+          const uint32_t at = atom_add(&sm.sel_n, 1u);
+          if (at < (uint32_t)OUTC) {
+            sm.o_logit[at] = g.logit[i]; sm.o_order[at] = g.order[i]; sm.o_aux[at] = g.aux[i];
+            sm.o_child[at] = g.child[i]; sm.o_info[at] = g.info[i];
+            g.order[i] |= 0x80000000u;  // mark: its key is copied after the histogram area is free
+            g.aux[i] = at;
+          }
+        }
+      }
+    }
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) {
+      for (uint32_t i = lane; i < n; i += NT)
+        if (g.order[i] & 0x80000000u) sm.o_key[g.aux[i]] = g.key[i];
+      if (lane == 0) sm.n_out[q] = sm.sel_n < (uint32_t)OUTC ? sm.sel_n : (uint32_t)OUTC;
+    }
+    CORAL_GSYNC(NT);
+  }
+
+  // ---- phase 3: prune, trim to beam_width, rank, write the next beam list -------------------
+  // rank = number of candidates that beat this one under (score desc, first-candidate index
+  // asc) -- pyctcdecode's stable heapq.nlargest. Candidates below the prune threshold never
+  // beat a survivor, so the count runs over the dense key array without any filter.
+  static CORAL_DEV void rank_and_commit(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                                        int cur, int q, unsigned long long thr, bool final_pass) {
+    const int nxt = cur ^ 1;
+    const uint32_t n = sm.n_out[q];
+    CORAL_LANES(NT) {
+      if (!final_pass) clear_hash(sm, lane);
+      for (uint32_t i = lane; i < n; i += NT) {
+        const unsigned long long ki = sm.o_key[i];
+        if (ki < thr) continue;
+        const uint32_t oi = sm.o_order[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+          const unsigned long long kj = sm.o_key[j];
+          r += kj > ki;
+          if (kj == ki) r += sm.o_order[j] < oi;
+        }
+        if (r >= (uint32_t)P.beam_width) continue;
+        atom_add(&sm.S[q], 1u);
+        const double logit = sm.o_logit[i];
+        if (final_pass) {
+          double comb;
+          {
+            unsigned long long u = ki;
+            u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
+            union { double d; unsigned long long u; } cv;
+            cv.u = u;
+            comb = cv.d;
+          }
+          sm.logit[nxt][r] = logit;
+          sm.lm_raw[nxt][r] = comb;        // final: combined score travels in lm_raw
+          sm.node[nxt][r] = sm.o_child[i];  // final: text node
+          continue;
+        }
+        const uint32_t info = sm.o_info[i];
+        const uint32_t rb = info & 0xFFFFu, c = (info >> 16) & 0xFFu, kf = info >> 24;
+        const uint32_t kind = kf & 3u;
+        const uint32_t lc = (int)c == P.blank_id ? kLcBlank : c;
         if (kind == 0 || kind == 1) {
-          const uint32_t src = kind == 0 ? rb : o.child;
+          const uint32_t src = kind == 0 ? rb : sm.o_child[i];
           const uint32_t mt = sm.meta[cur][src];
           sm.node[nxt][r] = sm.node[cur][src];
           sm.parent[nxt][r] = sm.parent[cur][src];
+          sm.gparent[nxt][r] = sm.gparent[cur][src];
           sm.bnd[nxt][r] = sm.bnd[cur][src];
           sm.wid[nxt][r] = sm.wid[cur][src];
           sm.whash[nxt][r] = sm.whash[cur][src];
           sm.lm_raw[nxt][r] = sm.lm_raw[cur][src];
-          sm.meta[nxt][r] = meta_pack(meta_tok(mt), lc, meta_flags(mt), meta_wlen(mt));
-        } else if (kind == 2) {
-          bool created;
-          const uint32_t nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, 0u, created);
-          unsigned long long h = sm.whash[cur][rb];
-          for (int q = 0; q < P.label_ncp[c]; ++q) h = word_hash_push(h, P.label_cps[c][q]);
-          sm.node[nxt][r] = nid;
-          sm.parent[nxt][r] = sm.node[cur][rb];
-          sm.bnd[nxt][r] = sm.bnd[cur][rb];
-          sm.wid[nxt][r] = o.aux;
-          sm.whash[nxt][r] = h;
-          sm.lm_raw[nxt][r] = sm.lm_raw[cur][rb];
-          sm.meta[nxt][r] = meta_pack(c, lc, (uint32_t)(o.kf >> 2), meta_wlen(sm.meta[cur][rb]) + P.label_ncp[c]);
+          sm.wlen[nxt][r] = sm.wlen[cur][src];
+          sm.meta[nxt][r] = meta_pack(meta_tok(mt), lc, meta_flags(mt), meta_ptok(mt));
         } else {
-          sm.node[nxt][r] = o.child;
+          const uint32_t pm = sm.meta[cur][rb];
           sm.parent[nxt][r] = sm.node[cur][rb];
-          sm.bnd[nxt][r] = o.aux;
-          sm.wid[nxt][r] = 0;
-          sm.whash[nxt][r] = kWordHashSeed;
-          sm.lm_raw[nxt][r] = lm.present ? sc.bnd[o.aux].lm_raw : 0.0;
-          sm.meta[nxt][r] = meta_pack(c, lc, 0u, 0u);
+          sm.gparent[nxt][r] = sm.parent[cur][rb];
+          if (kind == 2) {
+            unsigned long long h = sm.whash[cur][rb];
+            for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
+            const uint32_t wl = (uint32_t)sm.wlen[cur][rb] + P.label_ncp[c];
+            sm.node[nxt][r] = trie_get_or_add(sm, sc, sm.node[cur][rb], c, 0u);
+            sm.bnd[nxt][r] = sm.bnd[cur][rb];
+            sm.wid[nxt][r] = sm.o_aux[i];
+            sm.whash[nxt][r] = h;
+            sm.lm_raw[nxt][r] = sm.lm_raw[cur][rb];
+            sm.wlen[nxt][r] = (uint16_t)(wl > 65535u ? 65535u : wl);
+            sm.meta[nxt][r] = meta_pack(c, lc, kf >> 2, meta_tok(pm));
+          } else {
+            const uint32_t bn = sm.o_aux[i];
+            sm.node[nxt][r] = sm.o_child[i];
+            sm.bnd[nxt][r] = bn;
+            sm.wid[nxt][r] = 0;
+            sm.whash[nxt][r] = kWordHashSeed;
+            sm.lm_raw[nxt][r] = lm.present ? sc.bnd[bn].lm_raw : 0.0;
+            sm.wlen[nxt][r] = 0;
+            sm.meta[nxt][r] = meta_pack(c, lc, 0u, meta_tok(pm));
+          }
         }
-        sm.logit[nxt][r] = o.logit;
-      }
-    }
-    CORAL_GSYNC(NT);
-    CORAL_LANES(NT) {
-      if (lane == 0) {
-        uint32_t cnt = S > (uint32_t)P.beam_width ? (uint32_t)P.beam_width : S;
-        sm.nb = cnt;
-        sm.cur = nxt;
+        sm.logit[nxt][r] = logit;
       }
     }
     CORAL_GSYNC(NT);
   }
 
-  // ---- end of utterance ------------------------------------------------
-  static CORAL_DEV void finalize(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
-                                 const UttIO& io) {
-    build_node_hash(sm);
-    const int cur = sm.cur;
-    const uint32_t nN = sm.nN;
-    OutRec* outs = nN <= (uint32_t)OUTC ? sm.outs : sc.outs_g;
-    uint16_t* surv = nN <= (uint32_t)OUTC ? sm.surv : sc.surv_g;
-    // pass A: nodes with an open word (or the root) lead; they absorb their closed-word child
-    for (int pass = 0; pass < 2; ++pass) {
-      CORAL_LANES(NT) {
-        unsigned long long lmax = 0;
-        for (uint32_t j = lane; j < nN; j += NT) {
-          const int s = sm.ne_slot[j];
-          const uint32_t rb = rep_beam(sm, s);
-          const uint32_t mt = sm.meta[cur][rb];
-          const bool open_or_root = meta_wlen(mt) > 0 || meta_tok(mt) == kNoTok;
-          if (pass == 0 ? !open_or_root : (open_or_root || sm.claimed[s])) continue;
-          uint32_t mem[4];
-          int nm = 0;
-          if (sm.sb0[s] != kNone16) mem[nm++] = sm.sb0[s];
-          if (sm.sb1[s] != kNone16) mem[nm++] = sm.sb1[s];
-          if (pass == 0 && meta_wlen(mt) > 0) {
-            const int cs = h_find(sm, node_key(sm.node[cur][rb], (uint32_t)P.space_id));
-            if (cs >= 0) {
-              sm.claimed[cs] = 1;
-              if (sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
-              if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
-            }
-          }
-          OutRec o;
-          const uint32_t first = merge_members(sm, cur, mem, nm, 0.0, o.logit);
-          // logit + 0.0 is exact, so merge_members' "+ p" leaves the scores untouched
-          o.order = first;
-          const uint32_t last = mem[nm - 1];  // the later candidate's tuple is the one stored
-          const uint32_t lmt = sm.meta[cur][last];
-          double comb = o.logit;
-          if (lm.present) {
-            const bool open = meta_wlen(lmt) > 0;
-            const uint32_t lfl = meta_flags(lmt);
-            const bool in_lm = open && (lfl & kInLm);
-            const bool oov = !open || (lm.has_unigrams && !(lfl & kInUni)) || !in_lm;
-            LmState out;
-            const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][last]].st, in_lm ? sm.wid[cur][last] : 0u,
-                                            oov, true, out, io.stats);
-            comb = d_add(o.logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
-          }
-          o.comb = comb;
-          // text node: the open-word node itself, or the parent of a closed-word node
-          o.child = open_or_root ? sm.node[cur][rb] : sm.parent[cur][rb];
-          o.slot = (uint16_t)s;
-          o.c = 0;
-          o.kf = 0;
-          o.aux = 0;
-          outs[atom_add(&sm.n_out, 1u)] = o;
-          const unsigned long long ok = ordered_u64(o.comb);
-          lmax = ok > lmax ? ok : lmax;
-        }
-        if (lmax) atom_max_u64(&sm.gmax, lmax);
-      }
+  static CORAL_DEV unsigned long long prune_key(Sm& sm, const DecodeParams& P, int q) {
+    // max_score + beam_prune_logp in float64, back in key space
+    unsigned long long u = sm.gmax[q];
+    u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
+    union { double d; unsigned long long u; } c;
+    c.u = u;
+    return ordered_u64(d_add(c.d, P.beam_prune_logp));
+  }
+
+  // ---- one frame: 3 barriers on the common path ------------------------------------------------
+  static CORAL_DEV void frame_step(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc,
+                                   const UttIO& io, int f, int cur, int q, uint32_t nb) {
+    hash_beams(sm, cur, q, nb);
+    const uint32_t n_slots = sm.nN[q] * ((uint32_t)sm.nkept[f] + 1u);
+    const bool in_smem = n_slots <= (uint32_t)OUTC;
+    if (!in_smem && n_slots > sc.outs_cap) {
+      CORAL_LANES(NT) { if (lane == 0) sm.status = -4; }
       CORAL_GSYNC(NT);
+      return;
     }
-    select_and_commit(sm, lm, P, sc, outs, surv, true);
-    const int fin = sm.cur;
-    const uint32_t nf = sm.nb;
+    const OutView outs = in_smem ? smem_outs(sm) : sc.outs_g;
+    expand(sm, lm, P, sc, io, f, cur, q, nb, outs);
+    const unsigned long long thr = prune_key(sm, P, q);
+    if (!in_smem) select_overflow(sm, P, outs, q, thr);
+    rank_and_commit(sm, lm, P, sc, cur, q, thr, false);
+    trie_maybe_grow(sm, sc, P, io);
+  }
+
+  // ---- end of utterance ------------------------------------------------------
+  static CORAL_DEV uint32_t finalize(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                                     const UttIO& io, int cur, int q, uint32_t nb) {
+    hash_beams(sm, cur, q, nb);
+    const uint32_t nN = sm.nN[q];
+    const OutView outs = smem_outs(sm);  // nN <= beam_width <= OUTC
     CORAL_LANES(NT) {
-      if (lane == 0) { *io.out_n = (int32_t)nf; *io.out_status = sm.status; }
+      unsigned long long lmax = 0;
+      for (uint32_t j = lane; j < nN; j += NT) {
+        const int s = sm.ne_slot[j];
+        const uint32_t rb = rep_beam(sm, s);
+        const uint32_t mt = sm.meta[cur][rb];
+        const bool open_or_root = sm.wlen[cur][rb] > 0 || meta_tok(mt) == kNoTok;
+        // a closed-word node whose (open-word) parent is live is absorbed by the parent's group
+        if (!open_or_root && h_find(sm, node_key(sm.gparent[cur][rb], meta_ptok(mt))) >= 0) continue;
+        uint32_t mem[4];
+        int nm = 0;
+        if (sm.sb0[s] != kNone16) mem[nm++] = sm.sb0[s];
+        if (sm.sb1[s] != kNone16) mem[nm++] = sm.sb1[s];
+        if (sm.wlen[cur][rb] > 0) {
+          const int cs = h_find(sm, node_key(sm.node[cur][rb], (uint32_t)P.space_id));
+          if (cs >= 0) {
+            if (sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
+            if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
+          }
+        }
+        double logit;
+        // logit + 0.0 is exact, so merge_members' "+ p" leaves the scores untouched
+        const uint32_t first = merge_members(sm, cur, mem, nm, 0.0, logit);
+        const uint32_t last = mem[nm - 1];  // the later candidate's tuple is the one pyctcdecode keeps
+        double comb = logit;
+        if (lm.present) {
+          const bool open = sm.wlen[cur][last] > 0;
+          const uint32_t lfl = meta_flags(sm.meta[cur][last]);
+          const bool in_lm = open && (lfl & kInLm);
+          const bool oov = !open || (lm.has_unigrams && !(lfl & kInUni)) || !in_lm;
+          LmState out;
+          const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][last]].st, in_lm ? sm.wid[cur][last] : 0u, oov,
+                                          true, out, io.stats);
+          comb = d_add(logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
+        }
+        // text node: the open-word node itself, or the parent of a closed-word node
+        emit(sm, outs, q, comb, logit, first, 0u, open_or_root ? sm.node[cur][rb] : sm.parent[cur][rb], rb, 0u, 0u,
+             lmax);
+      }
+      if (lmax) atom_max_u64(&sm.gmax[q], lmax);
+    }
+    CORAL_GSYNC(NT);
+    rank_and_commit(sm, lm, P, sc, cur, q, prune_key(sm, P, q), true);
+    const int fin = cur ^ 1;
+    const uint32_t nf = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
+    CORAL_LANES(NT) {
+      if (lane == 0) {
+        *io.out_n = (int32_t)nf;
+        *io.out_status = sm.status;
+        if (io.stats) { atom_add(&io.stats[5], (unsigned long long)sm.node_count); atom_add(&io.stats[6], (unsigned long long)sm.bnd_count); }
+      }
       for (uint32_t r = lane; r < nf && r < (uint32_t)P.n_best; r += NT) {
         io.out_logit[r] = sm.logit[fin][r];
         io.out_comb[r] = sm.lm_raw[fin][r];
@@ -835,25 +861,32 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
+    return nf;
   }
 
-  // ---- whole utterance ---------------------------------------------------------------------
+  // ---- whole utterance ---------------------------------------------------------------------------
   static CORAL_DEV void decode(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc, const UttIO& io) {
     CORAL_LANES(NT) {
+      clear_hash(sm, lane);
       if (lane == 0) {
-        sm.cur = 0;
-        sm.nb = 1;
         sm.status = 0;
         sm.node_count = 1;
         sm.bnd_count = 1;
+        sm.ch_mask = (kChInit - 1u) < sc.ch_mask_max ? (kChInit - 1u) : sc.ch_mask_max;
+        sm.nN[0] = sm.nN[1] = 0;
+        sm.n_out[0] = sm.n_out[1] = 0;
+        sm.S[0] = sm.S[1] = 0;
+        sm.gmax[0] = sm.gmax[1] = 0;
         sm.logit[0][0] = 0.0;
         sm.lm_raw[0][0] = 0.0;
         sm.whash[0][0] = kWordHashSeed;
         sm.node[0][0] = 0;
         sm.parent[0][0] = kNoNode;
+        sm.gparent[0][0] = kNoNode;
         sm.bnd[0][0] = 0;
         sm.wid[0][0] = 0;
-        sm.meta[0][0] = meta_pack(kNoTok, 0xFFu, 0u, 0u);
+        sm.wlen[0][0] = 0;
+        sm.meta[0][0] = meta_pack(kNoTok, kLcNone, 0u, kNoTok);
         sc.node_parent[0] = kNoNode;
         sc.node_info[0] = kNoTok;
         if (lm.present) {
@@ -865,21 +898,26 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
-    for (int t0 = 0; t0 < io.T; t0 += kChunk) {
+    int cur = 0, q = 0;
+    uint32_t nb = 1;
+    bool failed = false;
+    for (int t0 = 0; t0 < io.T && !failed; t0 += kChunk) {
       const int nf = io.T - t0 < kChunk ? io.T - t0 : kChunk;
       stage_frames(sm, P, io, t0, nf);
       for (int f = 0; f < nf; ++f) {
-        frame_step(sm, lm, P, sc, io, f);
-        if (sm.status != 0) break;
+        frame_step(sm, lm, P, sc, io, f, cur, q, nb);
+        if (sm.status != 0) { failed = true; break; }
+        nb = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
+        cur ^= 1;
+        q ^= 1;
       }
-      if (sm.status != 0) break;
     }
-    if (sm.status != 0) {
+    if (failed) {
       CORAL_LANES(NT) { if (lane == 0) { *io.out_n = 0; *io.out_status = sm.status; } }
       CORAL_GSYNC(NT);
       return;
     }
-    finalize(sm, lm, P, sc, io);
+    finalize(sm, lm, P, sc, io, cur, q, nb);
   }
 };
 

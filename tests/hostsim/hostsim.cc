@@ -102,28 +102,34 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   memset(&lm, 0, sizeof(lm));
   if (d->has_lm) lm = make_view(d->lm, d->lx, d->lm.uni.data(), d->lm.ng.data(), d->lx.lex.data());
   SlotScratch sc;
-  sc.node_cap = (uint32_t)(2 * (size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 16);
-  sc.bnd_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 16);
-  uint32_t chs = 16;
+  sc.node_cap = (uint32_t)(2 * (size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
+  sc.bnd_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
+  uint32_t chs = 64;
   while (chs < 2 * sc.node_cap) chs <<= 1;
-  sc.ch_mask = chs - 1;
-  sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 16);
+  sc.ch_mask_max = chs - 1;
+  sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 64);
   std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap), ch_vals(chs);
   std::vector<unsigned long long> ch_keys(chs, 0ULL);
   std::vector<BndRec> bnd(sc.bnd_cap);
-  std::vector<OutRec> outs_g(sc.outs_cap);
-  std::vector<uint16_t> surv_g(sc.outs_cap);
+  std::vector<unsigned long long> g_key(sc.outs_cap);
+  std::vector<double> g_logit(sc.outs_cap);
+  std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
   sc.node_parent = node_parent.data();
   sc.node_info = node_info.data();
   sc.ch_keys = ch_keys.data();
   sc.ch_vals = ch_vals.data();
   sc.bnd = bnd.data();
-  sc.outs_g = outs_g.data();
-  sc.surv_g = surv_g.data();
+  sc.outs_g.key = g_key.data();
+  sc.outs_g.logit = g_logit.data();
+  sc.outs_g.order = g_order.data();
+  sc.outs_g.aux = g_aux.data();
+  sc.outs_g.child = g_child.data();
+  sc.outs_g.info = g_info.data();
+  sc.epoch = 0;
   int32_t status = 0;
   // decode the same utterance n_utt_repeat times on the same slot: exercises the epoch reuse
   for (int rep = 0; rep < n_utt_repeat; ++rep) {
-    sc.epoch = (uint32_t)(rep + 1);
+    sc.epoch += 1;
     UttIO io;
     io.logits = logits;
     io.T = T;
@@ -163,9 +169,9 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
   P.log_base_change = log_base_change;
   switch (variant) {
     case 0: if (beam_width > 128) break; return run<32, 128, 256>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
-    case 1: if (beam_width > 32) break; return run<32, 32, 16>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
+    case 1: if (beam_width > 32) break; return run<32, 32, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
     case 2: if (beam_width > 512) break; return run<128, 512, 1024>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
-    case 3: if (beam_width > 128) break; return run<64, 128, 64>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
+    case 3: if (beam_width > 128) break; return run<64, 128, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
     default: break;
   }
   g_err = "unsupported variant / beam width";

@@ -1,0 +1,146 @@
+"""CPU check of the beam-search KERNEL LOGIC (coral_b200/csrc/beam_core.h compiled with
+-DCORAL_HOSTSIM, lanes run sequentially) against the oracle. This validates the device
+algorithm -- node trie, gather-merge, LM records, prune/trim/rank, overflow path, child-table
+growth -- without a GPU; the `-m gpu` tests then check the real kernel through the C ABI."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import beams_equal
+
+
+@pytest.fixture(scope="module")
+def sim(small_lm, oracle_decoder):
+    from hostsim_lib import HostSim
+
+    return HostSim(oracle_decoder._alphabet.labels, small_lm[2])
+
+
+def _check(dec, hs, lg, **kw):
+    okw = {k: v for k, v in kw.items() if k in ("beam_width", "beam_prune_logp", "token_min_logp")}
+    dec.reset_params(alpha=kw.get("alpha", 0.5), beta=kw.get("beta", 1.5),
+                     unk_score_offset=kw.get("unk_score_offset", -10.0),
+                     lm_score_boundary=kw.get("score_boundary", True))
+    try:
+        ref = dec.decode_beams(lg, **okw)
+    finally:
+        dec.reset_params(alpha=0.5, beta=1.5, unk_score_offset=-10.0, lm_score_boundary=True)
+    got = hs.decode_beams(lg, **kw)
+    beams_equal(ref, got)
+
+
+def test_lm_sentence_scores_bit_exact(sim, oracle_decoder, small_lm, rng):
+    from coral_b200 import synth
+
+    words, model, _ = small_lm
+    m = oracle_decoder._language_model._kenlm_model
+    flat, lens = model.sample(150, "hs-lm")
+    for s in synth.sentences_to_text(flat, lens, words):
+        ws = s.split(" ")
+        if rng.random() < 0.5:
+            ws[int(rng.integers(len(ws)))] = "zzzqq"
+        st = m.begin_sentence_state()
+        ref = []
+        for w in ws:
+            p, st = m.base_score(st, w)
+            ref.append(p)
+        ref.append(m.base_score(st, "</s>")[0])
+        got, oov = sim.score_sentence(ws)
+        assert np.array_equal(np.array(ref, dtype=np.float32), got)
+        assert oov.tolist() == [int(w not in m) for w in ws]
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_peaky_utterances(sim, oracle_decoder, small_workload, variant):
+    w = small_workload
+    for u in range(6):
+        _check(oracle_decoder, sim, w.logits[u, : w.lengths[u]], variant=variant, repeat=2)
+
+
+def test_parameter_sweep(sim, oracle_decoder, small_workload):
+    w = small_workload
+    for u in range(3):
+        lg = w.logits[u, : w.lengths[u]]
+        _check(oracle_decoder, sim, lg, beam_width=20, variant=1)
+        _check(oracle_decoder, sim, lg, token_min_logp=-10.0, beam_prune_logp=-5.0)
+        _check(oracle_decoder, sim, lg, token_min_logp=-20.0, beam_width=64)
+        _check(oracle_decoder, sim, lg, alpha=0.9, beta=0.3, unk_score_offset=-4.0, score_boundary=False)
+
+
+def test_flat_logits_overflow_and_trim(sim, oracle_decoder, rng):
+    from coral_b200 import synth
+
+    flat = synth.flat_logits(50, rng)
+    _check(oracle_decoder, sim, flat)                              # overflow path (4k candidates / frame)
+    _check(oracle_decoder, sim, flat, beam_width=16, variant=1)
+    _check(oracle_decoder, sim, flat, variant=3)                   # small shared-memory candidate arrays
+    _check(oracle_decoder, sim, flat[:24], beam_width=512, variant=2)
+    _check(oracle_decoder, sim, flat[:30], beam_width=300, token_min_logp=-3.0, variant=2)
+
+
+def test_child_table_growth(sim, oracle_decoder, rng):
+    """Enough new prefixes per utterance to outgrow the initial 4096-entry child table."""
+    from coral_b200 import synth
+
+    lg = synth.flat_logits(120, rng)
+    _check(oracle_decoder, sim, lg, beam_width=100, repeat=2)
+    assert sim.last_stats[7] >= 1 and sim.last_stats[5] > 2048
+
+
+def test_edge_cases(sim, oracle_decoder, small_workload):
+    w = small_workload
+    _check(oracle_decoder, sim, np.zeros((0, 46), np.float32))
+    _check(oracle_decoder, sim, w.logits[0, :1])
+    _check(oracle_decoder, sim, w.logits[0, :2], beam_width=1, variant=1)
+    # -100-padded tail frames decoded as frames (what pyctcdecode does if they are not stripped)
+    lg = np.concatenate([w.logits[1, :40], np.full((5, 46), -100.0, np.float32)])
+    _check(oracle_decoder, sim, lg)
+
+
+def test_no_lm_and_unigram_variants(small_lm, small_workload, rng):
+    from coral_b200 import synth
+    from hostsim_lib import HostSim
+    from oracle.arpa import ArpaModel
+    from oracle.beam import Alphabet, BeamSearchDecoderCTC, build_ctcdecoder
+    from oracle.lm import LanguageModel
+
+    w = small_workload
+    words, _, path = small_lm
+    d0 = build_ctcdecoder(synth.CORAL_LABELS)
+    h0 = HostSim(d0._alphabet.labels)
+    _check(d0, h0, synth.flat_logits(40, rng))
+    _check(d0, h0, w.logits[0, : w.lengths[0]])
+    alpha = Alphabet.build_alphabet(synth.CORAL_LABELS)
+    dn = BeamSearchDecoderCTC(alpha, LanguageModel(ArpaModel.load(path), None))
+    _check(dn, HostSim(dn._alphabet.labels, path, unigrams=None), w.logits[1, : w.lengths[1]])
+    sub = sorted(set(words[:500]))
+    ds = BeamSearchDecoderCTC(alpha, LanguageModel(ArpaModel.load(path), sub))
+    _check(ds, HostSim(ds._alphabet.labels, path, unigrams=sub), w.logits[2, : w.lengths[2]])
+
+
+def test_probability_inputs(sim, oracle_decoder, small_workload):
+    import math
+
+    w = small_workload
+    z = w.logits[3, : w.lengths[3]].astype(np.float64)
+    p = np.exp(z - z.max(axis=1, keepdims=True))
+    p = (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+    if not math.isclose(float(p.sum(axis=1).mean()), 1):
+        pytest.skip("float32 mean of the row sums is not exactly 1 for this draw")
+    _check(oracle_decoder, sim, p)
+
+
+def test_work_counters_match_oracle(sim, oracle_decoder, small_workload):
+    """Device-side work counters agree with the oracle's: beam extensions and
+    frames exactly; LM word scorings = the oracle's cached_lm_scores misses."""
+    w = small_workload
+    lg = w.logits[4, : w.lengths[4]]
+    s0 = dict(oracle_decoder.stats)
+    oracle_decoder.decode_beams(lg)
+    d = {k: oracle_decoder.stats[k] - s0[k] for k in s0}
+    sim.decode_beams(lg)
+    st = sim.last_stats
+    assert int(st[0]) == d["extensions"] and int(st[3]) == d["frames"]
+    assert int(st[1]) == d["n_score"]
