@@ -31,7 +31,6 @@ struct BeamLaunch {
   uint8_t* scratch;
   unsigned long long slot_bytes;
   uint32_t node_cap, bnd_cap, ch_size, outs_cap;
-  uint32_t* slot_epoch;
   int32_t* work;
 };
 
@@ -42,8 +41,8 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
   size_t o = 0;
   off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
   off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
-  off[2] = o; o = align16(o + (size_t)ch_size * 8);        // ch_keys
-  off[3] = o; o = align16(o + (size_t)ch_size * 4);        // ch_vals
+  off[2] = o; o = align16(o + (size_t)ch_size * 8);        // child table (key << 32 | id)
+  off[3] = o;                                              // (unused)
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
   off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
   off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
@@ -54,7 +53,7 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
 // fetches the next from a global counter; `order` lets the host hand out long
 // utterances first so the tail of the batch is short.
 template <int NT, int BW, int OUTC>
-__global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
+__global__ void __launch_bounds__(NT, (768 / NT) > 0 ? (768 / NT) : 1) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Dec = BeamDecoder<NT, BW, OUTC>;
   typename Dec::Sm& sm = *reinterpret_cast<typename Dec::Sm*>(smem_raw);
@@ -66,8 +65,7 @@ __global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__
     uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
     sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
     sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
-    sc.ch_keys = reinterpret_cast<unsigned long long*>(base + off[2]);
-    sc.ch_vals = reinterpret_cast<uint32_t*>(base + off[3]);
+    sc.ch = reinterpret_cast<unsigned long long*>(base + off[2]);
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
     sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
     sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
@@ -80,14 +78,12 @@ __global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__
     sc.ch_mask_max = L.ch_size - 1;
     sc.outs_cap = L.outs_cap;
   }
-  sc.epoch = L.slot_epoch[slot];
   for (;;) {
     if (threadIdx.x == 0) sm.utt = atomicAdd(L.work, 1);
     group_sync<NT>();
     const int i = sm.utt;
     if (i >= L.B) break;
     const int u = L.order ? L.order[i] : i;
-    sc.epoch += 1;  // also bumped inside decode() when the child table grows
     UttIO io;
     io.logits = L.logits + (size_t)u * L.P.T_max * L.P.V;
     io.T = L.lengths[u];
@@ -102,7 +98,6 @@ __global__ void __launch_bounds__(NT) beam_search_kernel(const __grid_constant__
     Dec::decode(sm, L.lm, L.P, sc, io);
     group_sync<NT>();
   }
-  if (threadIdx.x == 0) L.slot_epoch[slot] = sc.epoch;
 }
 
 // ---- pyctcdecode's input check: math.isclose(logits.sum(axis=1).mean(), 1) -------------
@@ -198,18 +193,13 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
     // wait for earlier launches that may still use the old arena, then rebuild it
     CORAL_CUDA_OK(cudaDeviceSynchronize());
     if (dec->d_scratch) cudaFree(dec->d_scratch);
-    if (dec->d_slot_epoch) cudaFree(dec->d_slot_epoch);
     dec->d_scratch = nullptr;
-    dec->d_slot_epoch = nullptr;
     dec->scratch_bytes = 0;
     dec->n_slots = 0;
     const size_t bytes = sb * n_slots;
     CORAL_CUDA_OK(cudaMalloc(&dec->d_scratch, bytes));
-    CORAL_CUDA_OK(cudaMalloc(&dec->d_slot_epoch, sizeof(uint32_t) * n_slots));
-    CORAL_CUDA_OK(cudaMemsetAsync(dec->d_slot_epoch, 0, sizeof(uint32_t) * n_slots, st));
-    // child-table keys must start at 0 (= "never used"); everything else is written before read
-    for (uint32_t s = 0; s < n_slots; ++s)
-      CORAL_CUDA_OK(cudaMemsetAsync(dec->d_scratch + (size_t)s * sb + off[2], 0, (size_t)ch_size * 8, st));
+    // nothing to initialise: every arena is written before it is read (the kernel clears the
+    // part of the child table an utterance uses)
     dec->scratch_bytes = bytes;
     dec->slot_bytes = sb;
     dec->n_slots = n_slots;
@@ -226,7 +216,6 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   L.bnd_cap = bnd_cap;
   L.ch_size = ch_size;
   L.outs_cap = outs_cap;
-  L.slot_epoch = dec->d_slot_epoch;
   L.work = dec->d_work;
   const uint32_t grid = std::min<uint32_t>(dec->n_slots, std::max<uint32_t>(1, want));
   kern<<<grid, NT, smem, st>>>(L);
@@ -302,7 +291,6 @@ int32_t coral_decoder_free(coral_decoder* d) {
   cudaDeviceSynchronize();
   if (d->d_lex) cudaFree(d->d_lex);
   if (d->d_scratch) cudaFree(d->d_scratch);
-  if (d->d_slot_epoch) cudaFree(d->d_slot_epoch);
   if (d->d_work) cudaFree(d->d_work);
   if (d->d_rowsum) cudaFree(d->d_rowsum);
   if (d->d_is_prob) cudaFree(d->d_is_prob);

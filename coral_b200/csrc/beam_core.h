@@ -33,6 +33,7 @@ namespace coral {
 
 #if defined(CORAL_HOSTSIM)
 #define CORAL_DEV inline
+#define CORAL_DEV_OUTLINE inline
 template <class T>
 inline T atom_add(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline unsigned long long atom_max_u64(unsigned long long* p, unsigned long long v) {
@@ -41,10 +42,14 @@ inline unsigned long long atom_max_u64(unsigned long long* p, unsigned long long
 inline unsigned long long atom_cas_u64(unsigned long long* p, unsigned long long c, unsigned long long v) {
   unsigned long long o = *p; if (o == c) *p = v; return o;
 }
+inline uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
 #define CORAL_LANES(NT) for (int lane = 0; lane < (NT); ++lane)
 #define CORAL_GSYNC(NT) ((void)0)
 #else
 #define CORAL_DEV __device__ __forceinline__
+// bulky or rarely executed paths are kept out of line so that the per-frame loop stays
+// inside the instruction cache (the fully inlined kernel was 157 KB of SASS)
+#define CORAL_DEV_OUTLINE __device__ __noinline__
 template <class T>
 __device__ __forceinline__ T atom_add(T* p, T v) { return atomicAdd(p, v); }
 __device__ __forceinline__ unsigned long long atom_max_u64(unsigned long long* p, unsigned long long v) {
@@ -54,6 +59,7 @@ __device__ __forceinline__ unsigned long long atom_cas_u64(unsigned long long* p
                                                            unsigned long long v) {
   return atomicCAS(p, c, v);
 }
+__device__ __forceinline__ uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
 template <int NT>
 __device__ __forceinline__ void group_sync() {
   if (NT == 32) {
@@ -149,12 +155,10 @@ struct OutView {
 struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after utterance
   uint32_t* node_parent;
   uint32_t* node_info;  // tok | bnd << 8
-  unsigned long long* ch_keys;  // epoch << 32 | parent << 8 | tok ; 0 = never used
-  uint32_t* ch_vals;
+  unsigned long long* ch;  // child table: node_key32(parent, tok) << 32 | node id ; 0 = empty
   BndRec* bnd;
   OutView outs_g;       // overflow for frames with more candidates than fit in smem
   uint32_t node_cap, bnd_cap, ch_mask_max, outs_cap;
-  uint32_t epoch;       // bumped per utterance and per child-table growth
 };
 
 struct UttIO {
@@ -168,12 +172,14 @@ struct UttIO {
   uint8_t* out_tokens;  // [n_best, T_max]
   int32_t* out_len;     // [n_best]
   int32_t* out_status;  // scalar: 0 ok, -4 capacity
-  // optional [8]: extensions, LM scorings, n-gram probes, frames, lexicon probes, trie nodes,
-  // LM boundary records, child-table growths
+  // optional [16]: extensions, LM scorings, n-gram probes, frames, lexicon probes, trie nodes,
+  // LM boundary records, child-table growths; [8..15] cycles per phase (thread 0): hash, expand,
+  // overflow select, bucket, scatter, rank+commit, grow, frame staging
   unsigned long long* stats;
 };
 
-constexpr uint32_t kChInit = 4096;  // initial child-table size per utterance (grows x4)
+constexpr uint32_t kChMin = 1024;   // smallest child table; sized ~48 entries per frame, grows x4
+constexpr int kNB = 64;             // score buckets over the prune window
 
 template <int BW, int OUTC>
 struct GroupShared {
@@ -190,7 +196,7 @@ struct GroupShared {
   uint32_t meta[2][BW];  // tok | lc << 8 | flags << 16 | parent's tok << 24
   uint16_t wlen[2][BW];
   // live-node hash
-  unsigned long long hkey[HS];
+  uint32_t hkey[HS];
   uint16_t sb0[HS], sb1[HS];
   uint16_t ne_slot[BW];
   // candidates of this frame (also reused as the 256-bin histogram of the overflow path)
@@ -200,19 +206,30 @@ struct GroupShared {
   uint32_t o_aux[OUTC];
   uint32_t o_child[OUTC];
   uint32_t o_info[OUTC];
+  // score buckets for ranking (phase 3)
+  uint32_t bcnt[kNB];
+  uint32_t gcnt[kNB / 8];
+  uint16_t o_pos[OUTC];     // position of a candidate inside its bucket
+  uint8_t o_bkt[OUTC];      // its bucket
+  uint16_t o_sorted[OUTC];  // survivors grouped by bucket (counting sort)
   // staged frames
   float lp[kChunk][kVMax];
   uint8_t kept[kChunk][kVMax];
   uint8_t nkept[kChunk];
+  uint8_t amax[kChunk];
   // scalars; the per-frame counters are double-buffered by frame parity so that the next
   // frame's copy can be cleared without an extra barrier
   unsigned long long gmax[2];
+  double mhat;  // reference score of this frame's buckets: an estimate of its best score
   unsigned long long sel_prefix, sel_mask;
   uint32_t nN[2], n_out[2], S[2];
   uint32_t node_count, bnd_count, ch_mask;
   uint32_t sel_need, sel_eq, sel_cut, sel_n;
   uint32_t gsum[16];
   int32_t status, utt;
+  uint32_t cnt[8];  // work counters of this utterance (flushed to UttIO::stats at its end)
+  unsigned long long opc[8];  // tuning: cycles spent inside selected device operations
+  uint32_t opn[8];            //         and how many times each ran
 };
 
 CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags, uint32_t ptok) {
@@ -225,38 +242,84 @@ CORAL_HD uint32_t meta_ptok(uint32_t m) { return m >> 24; }
 constexpr uint32_t kLcNone = 0xFFu;   // last_char None (start of utterance)
 constexpr uint32_t kLcBlank = 0xFEu;  // last_char "" (blank)
 
-CORAL_HD unsigned long long node_key(uint32_t parent, uint32_t tok) {
-  // root is (kNoNode, kNoTok); +1 keeps every key non-zero
-  return (((unsigned long long)parent << 8) | tok) + 1ULL;
+CORAL_HD uint32_t node_key(uint32_t parent, uint32_t tok) {
+  // (parent + 1) in 24 bits, token in 8: the root (kNoNode, kNoTok) maps to 0xFF and no key is 0
+  return (((parent + 1u) & 0xFFFFFFu) << 8) | tok;
 }
 
 // pyctcdecode LanguageModel.score_partial_token, hotwords empty
-CORAL_HD double partial_score(const DecodeParams& P, uint32_t wlen, uint32_t flags) {
+static CORAL_DEV_OUTLINE double partial_score_long(double u, uint32_t wlen) { return d_div(d_mul(u, (double)wlen), 6.0); }
+CORAL_DEV double partial_score(const DecodeParams& P, uint32_t wlen, uint32_t flags) {
   if (wlen == 0) return 0.0;
-  double u = d_mul(P.unk_score_offset, (flags & kOovPartial) ? 1.0 : 0.0);
-  if (wlen > 6) u = d_div(d_mul(u, (double)wlen), 6.0);
-  return u;
+  const double u = d_mul(P.unk_score_offset, (flags & kOovPartial) ? 1.0 : 0.0);
+  return wlen > 6 ? partial_score_long(u, wlen) : u;
 }
 
 // pyctcdecode LanguageModel.score: alpha * log10-score * ln10 + beta
-CORAL_DEV double lm_word_score(const LmView& lm, const DecodeParams& P, const LmState& in, uint32_t wid,
-                               bool oov, bool is_last, LmState& out, unsigned long long* stats) {
+static CORAL_DEV_OUTLINE float lm_base_score_call(const LmView& lm, const LmState& in, uint32_t w, LmState& out,
+                                                  int* probes) {
+  return lm_base_score(lm, in, w, out, probes);
+}
+static CORAL_DEV_OUTLINE double lm_word_score(const LmView& lm, const DecodeParams& P, const LmState& in, uint32_t wid,
+                               bool oov, bool is_last, LmState& out, uint32_t* cnt) {
   int np = 0;
-  double x = (double)lm_base_score(lm, in, wid, out, &np);
+  double x = (double)lm_base_score_call(lm, in, wid, out, &np);
   if (oov) x = d_add(x, P.unk_score_offset);
   if (is_last) {
     double e = 0.0;
     if (P.score_boundary) {
       LmState tmp;
       int np2 = 0;
-      e = (double)lm_base_score(lm, out, lm.eos_id, tmp, &np2);
+      e = (double)lm_base_score_call(lm, out, lm.eos_id, tmp, &np2);
       np += np2;
     }
     x = d_add(x, e);
   }
-  if (stats) { atom_add(&stats[1], 1ULL); atom_add(&stats[2], (unsigned long long)np); }
+  if (cnt) { atom_add(&cnt[1], 1u); atom_add(&cnt[2], (uint32_t)np); }
   return d_add(d_mul(d_mul(P.alpha, x), P.log_base_change), P.beta);
 }
+
+// Op timing for tuning: average latency of selected operations (trie find / insert, LM word
+// scoring, lexicon probe, merge) as seen by the calling thread, under the real load.
+#if defined(__CUDA_ARCH__)
+#define CORAL_OP_T0(on) const long long _t0 = (on) ? clock64() : 0
+#define CORAL_OP_T1(on, sm, slot)                                                      \
+  do {                                                                                 \
+    if (on) {                                                                          \
+      atomicAdd(&(sm).opc[slot], (unsigned long long)(clock64() - _t0));               \
+      atomicAdd(&(sm).opn[slot], 1u);                                                  \
+    }                                                                                  \
+  } while (0)
+#else
+#define CORAL_OP_T0(on) (void)0
+#define CORAL_OP_T1(on, sm, slot) (void)0
+#endif
+
+// Phase timing for tuning: when a stats buffer is passed, thread 0 of the group adds the
+// cycles between two marks to stats[slot] (slots 8..15). Costs nothing when stats == nullptr.
+struct PhaseTimer {
+  long long t;
+  unsigned long long* stats;
+  CORAL_DEV void start(unsigned long long* st) {
+    stats = st;
+#if defined(__CUDA_ARCH__)
+    t = (st && threadIdx.x == 0) ? clock64() : 0;
+#else
+    t = 0;
+#endif
+  }
+  CORAL_DEV void mark(int slot) {
+#if defined(__CUDA_ARCH__)
+    if (stats && threadIdx.x == 0) {
+      const long long n = clock64();
+      atomicAdd(&stats[slot], (unsigned long long)(n - t));
+      t = n;
+    }
+#else
+    (void)slot;
+#endif
+  }
+};
 
 template <int NT, int BW, int OUTC>
 struct BeamDecoder {
@@ -264,20 +327,21 @@ struct BeamDecoder {
   static constexpr int HS = Sm::HS;
 
   // ---- live-node hash (shared memory) ------------------------------------------------
-  static CORAL_DEV int h_find(Sm& sm, unsigned long long key) {
-    uint32_t i = (uint32_t)mix64(key) & (HS - 1);
+  static CORAL_DEV uint32_t h_slot(uint32_t key) { return (key * 0x9E3779B1u) >> 7; }
+  static CORAL_DEV int h_find(Sm& sm, uint32_t key) {
+    uint32_t i = h_slot(key) & (HS - 1);
     for (;;) {
-      const unsigned long long k = sm.hkey[i];
+      const uint32_t k = sm.hkey[i];
       if (k == key) return (int)i;
       if (k == 0) return -1;
       i = (i + 1) & (HS - 1);
     }
   }
   // returns the slot; `created` tells the caller it is the one that inserted the key
-  static CORAL_DEV int h_insert(Sm& sm, unsigned long long key, bool& created) {
-    uint32_t i = (uint32_t)mix64(key) & (HS - 1);
+  static CORAL_DEV int h_insert(Sm& sm, uint32_t key, bool& created) {
+    uint32_t i = h_slot(key) & (HS - 1);
     for (;;) {
-      const unsigned long long k = atom_cas_u64(&sm.hkey[i], 0ULL, key);
+      const uint32_t k = atom_cas_u32(&sm.hkey[i], 0u, key);
       if (k == 0) { created = true; return (int)i; }
       if (k == key) { created = false; return (int)i; }
       i = (i + 1) & (HS - 1);
@@ -285,70 +349,77 @@ struct BeamDecoder {
   }
 
   // ---- per-utterance trie child table (HBM) ------------------------------------------
-  // Keys carry the slot's epoch, so entries of earlier utterances (or of the table before
-  // it grew) read as empty and nothing is ever cleared.
-  static CORAL_DEV unsigned long long ch_key(const SlotScratch& sc, uint32_t parent, uint32_t tok) {
-    return ((unsigned long long)sc.epoch << 32) | ((unsigned long long)(parent & 0xFFFFFFu) << 8) | tok;
-  }
-  static CORAL_DEV void ch_put(Sm& sm, const SlotScratch& sc, unsigned long long key, uint32_t id) {
-    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
-    for (;;) {
-      const unsigned long long k = sc.ch_keys[i];
-      if ((k >> 32) != sc.epoch) {
-        if (atom_cas_u64(&sc.ch_keys[i], k, key) == k) { sc.ch_vals[i] = id; return; }
-        continue;  // lost the slot to another lane: look at it again
-      }
-      i = (i + 1) & sm.ch_mask;
-    }
-  }
+  // One 64-bit word per slot, key in the high half and node id in the low half, cleared at
+  // the start of the utterance: a lookup is one load and an insert is one compare-and-swap
+  // with no prior load (the dependent round trips to HBM/L2 are the critical path here).
+  static CORAL_DEV uint32_t ch_slot(uint32_t key) { return (uint32_t)mix64(key); }
   // Returns the node id of (parent, tok), creating it if absent.
-  static CORAL_DEV uint32_t trie_get_or_add(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok,
-                                            uint32_t bnd) {
-    const unsigned long long key = ch_key(sc, parent, tok);
-    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
-    uint32_t id = kNoNode;
+  static CORAL_DEV_OUTLINE uint32_t trie_get_or_add(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok,
+                                                    uint32_t bnd) {
+    const uint32_t key = node_key(parent, tok);
+    const uint32_t id = atom_add(&sm.node_count, 1u);
+    if (id >= sc.node_cap) { sm.status = -4; return 0; }
+    const unsigned long long mine = ((unsigned long long)key << 32) | id;
+    uint32_t i = ch_slot(key) & sm.ch_mask;
     for (;;) {
-      const unsigned long long k = sc.ch_keys[i];
-      if (k == key) return sc.ch_vals[i];
-      if ((k >> 32) != sc.epoch) {  // empty or stale
-        if (id == kNoNode) id = atom_add(&sm.node_count, 1u);
-        if (id >= sc.node_cap) { sm.status = -4; return 0; }
-        if (atom_cas_u64(&sc.ch_keys[i], k, key) == k) {
-          sc.ch_vals[i] = id;
-          sc.node_parent[id] = parent;
-          sc.node_info[id] = tok | (bnd << 8);
-          return id;
-        }
-        continue;  // lost the slot to another lane (a different key: keys are unique per frame)
+      const unsigned long long old = atom_cas_u64(&sc.ch[i], 0ULL, mine);
+      if (old == 0) {
+        sc.node_parent[id] = parent;
+        sc.node_info[id] = tok | (bnd << 8);
+        return id;
+      }
+      if ((uint32_t)(old >> 32) == key) {  // already there: the fresh id stays unused (marked so a
+        sc.node_parent[id] = kNoNode;      // later table growth skips it)
+        sc.node_info[id] = kNoTok;
+        return (uint32_t)old;
       }
       i = (i + 1) & sm.ch_mask;
     }
   }
-  static CORAL_DEV bool trie_find(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok, uint32_t& id) {
-    const unsigned long long key = ch_key(sc, parent, tok);
-    uint32_t i = (uint32_t)mix64(key) & sm.ch_mask;
+  static CORAL_DEV_OUTLINE bool trie_find(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok, uint32_t& id) {
+    const uint32_t key = node_key(parent, tok);
+    uint32_t i = ch_slot(key) & sm.ch_mask;
     for (;;) {
-      const unsigned long long k = sc.ch_keys[i];
-      if (k == key) { id = sc.ch_vals[i]; return true; }
-      if ((k >> 32) != sc.epoch) return false;
+      const unsigned long long w = sc.ch[i];
+      if (w == 0) return false;
+      if ((uint32_t)(w >> 32) == key) { id = (uint32_t)w; return true; }
       i = (i + 1) & sm.ch_mask;
     }
   }
-  // Keep the child table at most half full: grow x4 (new epoch, re-insert every node).
+  static CORAL_DEV void trie_clear(Sm& sm, const SlotScratch& sc, uint32_t size) {
+    CORAL_LANES(NT) {
+#pragma unroll 2
+      for (uint32_t i = lane; i < size; i += NT) sc.ch[i] = 0ULL;
+      if (lane == 0) sm.ch_mask = size - 1u;
+    }
+    CORAL_GSYNC(NT);
+  }
+  // Keep the child table at most half full: grow x4 and re-insert every node.
   static CORAL_DEV void trie_maybe_grow(Sm& sm, SlotScratch& sc, const DecodeParams& P, const UttIO& io) {
     const uint32_t need = (sm.node_count + 2u * (uint32_t)P.beam_width + 2u) * 2u;
     if (need <= sm.ch_mask + 1u || sm.ch_mask >= sc.ch_mask_max) return;  // uniform: read after a barrier
+    trie_grow(sm, sc, io, need);
+  }
+  static CORAL_DEV_OUTLINE void trie_grow(Sm& sm, SlotScratch& sc, const UttIO& io, uint32_t need) {
     uint32_t size = sm.ch_mask + 1u;
     while (size < need && size - 1u < sc.ch_mask_max) size <<= 2;
     if (size - 1u > sc.ch_mask_max) size = sc.ch_mask_max + 1u;
     CORAL_GSYNC(NT);
-    CORAL_LANES(NT) { if (lane == 0) { sm.ch_mask = size - 1u; if (io.stats) atom_add(&io.stats[7], 1ULL); } }
-    sc.epoch += 1;
-    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) { if (lane == 0 && io.stats) sm.cnt[7] += 1u; }
+    trie_clear(sm, sc, size);
     const uint32_t n = sm.node_count;
     CORAL_LANES(NT) {
-      for (uint32_t id = 1 + lane; id < n; id += NT)
-        ch_put(sm, sc, ch_key(sc, sc.node_parent[id], sc.node_info[id] & 0xFFu), id);
+      for (uint32_t id = 1 + lane; id < n; id += NT) {
+        if (sc.node_parent[id] == kNoNode) continue;  // unused id
+        const uint32_t key = node_key(sc.node_parent[id], sc.node_info[id] & 0xFFu);
+        const unsigned long long mine = ((unsigned long long)key << 32) | id;
+        uint32_t i = ch_slot(key) & sm.ch_mask;
+        for (;;) {
+          const unsigned long long old = atom_cas_u64(&sc.ch[i], 0ULL, mine);
+          if (old == 0 || (uint32_t)(old >> 32) == key) break;
+          i = (i + 1) & sm.ch_mask;
+        }
+      }
     }
     CORAL_GSYNC(NT);
   }
@@ -357,55 +428,119 @@ struct BeamDecoder {
   // x_max, tmp = x - x_max, exp, sum (numpy pairwise order for a
   // contiguous row of n <= 128: eight strided accumulators, combined as a balanced tree,
   // remainder added in order), log, tmp - log, clip to [log(1e-15), 0].
-  static CORAL_DEV void stage_frames(Sm& sm, const DecodeParams& P, const UttIO& io, int t0, int nf) {
+  static CORAL_DEV_OUTLINE void stage_frames(Sm& sm, const DecodeParams& P, const UttIO& io, int t0, int nf) {
     const int V = P.V;
     CORAL_LANES(NT) {
+#pragma unroll 2
       for (int i = lane; i < nf * V; i += NT) sm.lp[i / V][i % V] = io.logits[(size_t)t0 * V + i];
     }
     CORAL_GSYNC(NT);
     const float lo = -34.538776f;  // float32(log(1e-15))
     const bool as_prob = P.input_mode == 2 || (P.input_mode == 0 && io.is_prob);
-    CORAL_LANES(NT) {
-      for (int f = lane; f < nf; f += NT) {
-        float* row = sm.lp[f];
-        if (as_prob) {
-          for (int v = 0; v < V; ++v) {
-            float x = row[v];
-            x = x < 1e-15f ? 1e-15f : (x > 1.0f ? 1.0f : x);
-            row[v] = logf(x);
-          }
-        } else {
+    if (as_prob) {
+      CORAL_LANES(NT) {
+        for (int i = lane; i < nf * V; i += NT) {
+          float x = sm.lp[i / V][i % V];
+          x = x < 1e-15f ? 1e-15f : (x > 1.0f ? 1.0f : x);
+          sm.lp[i / V][i % V] = logf(x);
+        }
+      }
+      CORAL_GSYNC(NT);
+    } else if (V < 8) {
+      CORAL_LANES(NT) {
+        for (int f = lane; f < nf; f += NT) {
+          float* row = sm.lp[f];
           float mx = row[0];
           for (int v = 1; v < V; ++v) mx = row[v] > mx ? row[v] : mx;
           if (!isfinite(mx)) mx = 0.0f;
-          float r[8];
-          float s;
-          if (V < 8) {
-            s = 0.0f;
-            for (int v = 0; v < V; ++v) { row[v] = f32_add(row[v], -mx); s = f32_add(s, expf(row[v])); }
-          } else {
-            for (int j = 0; j < 8; ++j) { row[j] = f32_add(row[j], -mx); r[j] = expf(row[j]); }
-            int i = 8;
-            for (; i < V - (V % 8); i += 8)
-              for (int j = 0; j < 8; ++j) { row[i + j] = f32_add(row[i + j], -mx); r[j] = f32_add(r[j], expf(row[i + j])); }
-            s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])),
-                        f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
-            for (; i < V; ++i) { row[i] = f32_add(row[i], -mx); s = f32_add(s, expf(row[i])); }
-          }
+          float s = 0.0f;
+          for (int v = 0; v < V; ++v) { row[v] = f32_add(row[v], -mx); s = f32_add(s, expf(row[v])); }
           const float ls = logf(s);
           for (int v = 0; v < V; ++v) {
-            float y = f32_add(row[v], -ls);
+            const float y = f32_add(row[v], -ls);
             row[v] = y < lo ? lo : (y > 0.0f ? 0.0f : y);
           }
         }
-        // argmax (first maximum) and the kept-token list in ascending id
+      }
+      CORAL_GSYNC(NT);
+    } else {
+      // eight lanes per frame: lane j owns numpy's accumulator r[j] (elements j, j+8, ...)
+      float* pmax = reinterpret_cast<float*>(sm.o_logit);  // [kChunk][8], candidate arrays are idle here
+      float* racc = pmax + kChunk * 8;                     // [kChunk][8]
+      const int main_n = V - (V % 8);
+      CORAL_LANES(NT) {
+        for (int p = lane; p < nf * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          const float* row = sm.lp[f];
+          float m = row[j];
+#pragma unroll 1
+          for (int i = j + 8; i < V; i += 8) m = row[i] > m ? row[i] : m;
+          pmax[p] = m;
+        }
+      }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        for (int p = lane; p < nf * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          float* row = sm.lp[f];
+          float mx = pmax[f * 8];
+#pragma unroll 1
+          for (int k = 1; k < 8; ++k) mx = pmax[f * 8 + k] > mx ? pmax[f * 8 + k] : mx;
+          if (!isfinite(mx)) mx = 0.0f;
+          row[j] = f32_add(row[j], -mx);
+          float r = expf(row[j]);
+#pragma unroll 1
+          for (int i = j + 8; i < main_n; i += 8) { row[i] = f32_add(row[i], -mx); r = f32_add(r, expf(row[i])); }
+          racc[p] = r;
+          if (main_n + j < V) row[main_n + j] = f32_add(row[main_n + j], -mx);  // remainder: summed in order below
+        }
+      }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        for (int p = lane; p < nf * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          float* row = sm.lp[f];
+          const float* r = racc + f * 8;
+          float s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])),
+                            f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
+#pragma unroll 1
+          for (int i = main_n; i < V; ++i) s = f32_add(s, expf(row[i]));
+          const float ls = logf(s);
+          // every lane of the frame computed the same ls; each clips its own elements, but only
+          // after all eight have read the remainder values -> written in the next phase
+          pmax[p] = ls;
+          (void)j;
+        }
+      }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        for (int p = lane; p < nf * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          float* row = sm.lp[f];
+          const float ls = pmax[p];
+#pragma unroll 1
+          for (int i = j; i < V; i += 8) {
+            const float y = f32_add(row[i], -ls);
+            row[i] = y < lo ? lo : (y > 0.0f ? 0.0f : y);
+          }
+        }
+      }
+      CORAL_GSYNC(NT);
+    }
+    // argmax (first maximum) and the kept-token list in ascending id
+    CORAL_LANES(NT) {
+      for (int f = lane; f < nf; f += NT) {
+        const float* row = sm.lp[f];
         int am = 0;
         float best = row[0];
+#pragma unroll 1
         for (int v = 1; v < V; ++v) if (row[v] > best) { best = row[v]; am = v; }
         int nk = 0;
+#pragma unroll 1
         for (int v = 0; v < V; ++v)
           if (row[v] >= P.token_min_logp || v == am) sm.kept[f][nk++] = (uint8_t)v;
         sm.nkept[f] = (uint8_t)nk;
+        sm.amax[f] = (uint8_t)am;
       }
     }
     CORAL_GSYNC(NT);
@@ -415,7 +550,7 @@ struct BeamDecoder {
 
   // Sequential log-sum-exp of (logit[b] + p) over up to four member beams in ascending
   // beam index (= the reference's candidate order within one token). Returns min index.
-  static CORAL_DEV uint32_t merge_members(Sm& sm, int cur, uint32_t m[4], int n, double p, double& score) {
+  static CORAL_DEV_OUTLINE uint32_t merge_members(Sm& sm, int cur, uint32_t m[4], int n, double p, double& score) {
     for (int a = 1; a < n; ++a) {  // insertion sort of <= 4 indices
       uint32_t x = m[a];
       int b = a - 1;
@@ -433,8 +568,24 @@ struct BeamDecoder {
     o.info = sm.o_info;
     return o;
   }
-  static CORAL_DEV void emit(Sm& sm, const OutView& o, int q, double comb, double logit, uint32_t order, uint32_t aux,
-                             uint32_t child, uint32_t rb, uint32_t c, uint32_t kf, unsigned long long& lmax) {
+  static CORAL_DEV double key_to_double(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
+    union { double d; unsigned long long u; } cv;
+    cv.u = u;
+    return cv.d;
+  }
+  // Score bucket, monotone in the score: floor((mhat - score) * scale) clamped to [0, kNB).
+  // Any monotone map keeps the ranking exact; mhat only has to spread the survivors.
+  static CORAL_DEV uint32_t bucket_of(double mhat, double scale, double comb) {
+    const double d = d_mul(d_add(mhat, -comb), scale);
+    return d >= (double)(kNB - 1) ? (uint32_t)(kNB - 1) : (d > 0.0 ? (uint32_t)d : 0u);
+  }
+  static CORAL_DEV double bucket_scale(const DecodeParams& P) {
+    return d_div((double)kNB, d_add(P.beam_prune_logp < 0.0 ? -P.beam_prune_logp : 0.0, 4.0));
+  }
+  static CORAL_DEV_OUTLINE void emit(Sm& sm, const OutView& o, int q, bool hist, double scale, double comb, double logit,
+                             uint32_t order, uint32_t aux, uint32_t child, uint32_t rb, uint32_t c, uint32_t kf,
+                             unsigned long long& lmax) {
     const uint32_t at = atom_add(&sm.n_out[q], 1u);
     const unsigned long long k = ordered_u64(comb);
     o.key[at] = k;
@@ -443,15 +594,27 @@ struct BeamDecoder {
     o.aux[at] = aux;
     o.child[at] = child;
     o.info[at] = rb | (c << 16) | (kf << 24);
+    if (hist) {  // counting-sort histogram for phase 3 (shared-memory path only)
+      const uint32_t b = bucket_of(sm.mhat, scale, comb);
+      sm.o_pos[at] = (uint16_t)atom_add(&sm.bcnt[b], 1u);
+      sm.o_bkt[at] = (uint8_t)b;
+      atom_add(&sm.gcnt[b >> 3], 1u);
+    }
     lmax = k > lmax ? k : lmax;
   }
 
   // ---- phase 1: hash the live nodes of the current beam list -----------------------------
   // The hash was cleared during the previous frame's phase 3. The lane whose CAS inserts a
   // node registers it in the node list; every beam records itself in its node's slot.
-  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb) {
+  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb, double best_lp) {
     CORAL_LANES(NT) {
-      if (lane == 0) { sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0; }
+      if (lane == 0) {
+        // bucket reference for this frame: last frame's best score + this frame's best
+        // log-prob (+2: merges and word completions can raise a score a little)
+        sm.mhat = d_add(d_add(key_to_double(sm.gmax[q ^ 1]), best_lp), 2.0);
+      }
+      for (int i = lane; i < kNB; i += NT) sm.bcnt[i] = 0;
+      for (int i = lane; i < kNB / 8; i += NT) sm.gcnt[i] = 0;
       for (uint32_t b = lane; b < nb; b += NT) {
         const uint32_t mt = sm.meta[cur][b];
         bool created;
@@ -469,11 +632,18 @@ struct BeamDecoder {
 
   // ---- phase 2: every (live node, kept token), plus repeats of nodes whose parent is dead ---
   static CORAL_DEV void expand(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
-                               const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs) {
+                               const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs,
+                               bool hist) {
     const int K = sm.nkept[f];
+    const double bscale = bucket_scale(P);
     const uint32_t nN = sm.nN[q];
     CORAL_LANES(NT) {
-      if (lane == 0 && io.stats) { atom_add(&io.stats[0], (unsigned long long)K * nb); atom_add(&io.stats[3], 1ULL); }
+      if (lane == 0) {
+        // clear the other parity's per-frame counters for the next frame. This must sit behind
+        // this frame's first barrier: every thread read S[q ^ 1] (the beam count) on its way in.
+        sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
+        if (io.stats) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
+      }
       unsigned long long lmax = 0;
       const uint32_t n1 = nN * (uint32_t)K;
       for (uint32_t i = lane; i < n1 + nN; i += NT) {
@@ -499,7 +669,7 @@ struct BeamDecoder {
           if ((int)c == P.space_id && b0 != kNone16) mem[nm++] = b0;
           if (nm == 0) continue;
           const uint32_t first = merge_members(sm, cur, mem, nm, (double)sm.lp[f][c], logit);
-          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
                (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax);
           continue;
         }
@@ -510,7 +680,7 @@ struct BeamDecoder {
           if (b0 != kNone16) mem[nm++] = b0;
           if (b1 != kNone16) mem[nm++] = b1;
           const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
-          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
                k * nb + first, 0u, 0u, rb, c, 0u, lmax);
           continue;
         }
@@ -527,7 +697,7 @@ struct BeamDecoder {
         const uint32_t order = k * nb + first;
         if (cs >= 0) {
           const uint32_t crb = rep_beam(sm, cs);
-          emit(sm, outs, q,
+          emit(sm, outs, q, hist, bscale,
                d_add(logit, d_add(sm.lm_raw[cur][crb],
                                   partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])))),
                logit, order, 0u, crb, rb, c, 1u, lmax);
@@ -536,7 +706,9 @@ struct BeamDecoder {
           // record, like pyctcdecode's cached_lm_scores entry for the new text)
           uint32_t nid = 0, bnd_new = 0;
           double raw_new = sm.lm_raw[cur][rb];
-          if (trie_find(sm, sc, sm.node[cur][rb], c, nid)) {
+          bool have;
+          { CORAL_OP_T0(io.stats != nullptr); have = trie_find(sm, sc, sm.node[cur][rb], c, nid); CORAL_OP_T1(io.stats != nullptr, sm, 0); }
+          if (have) {
             bnd_new = sc.node_info[nid] >> 8;
             if (lm.present) raw_new = sc.bnd[bnd_new].lm_raw;
           } else {
@@ -546,15 +718,17 @@ struct BeamDecoder {
               const bool in_lm = (fl_m & kInLm) != 0;
               const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
               BndRec nr;
+              CORAL_OP_T0(io.stats != nullptr);
               const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u, oov,
-                                              false, nr.st, io.stats);
+                                              false, nr.st, io.stats ? sm.cnt : nullptr);
+              CORAL_OP_T1(io.stats != nullptr, sm, 1);
               nr.lm_raw = d_add(sm.lm_raw[cur][rb], sw);
               raw_new = nr.lm_raw;
               sc.bnd[bnd_new] = nr;
             }
-            nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, bnd_new);
+            { CORAL_OP_T0(io.stats != nullptr); nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, bnd_new); CORAL_OP_T1(io.stats != nullptr, sm, 2); }
           }
-          emit(sm, outs, q, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, nid, rb, c, 3u, lmax);
+          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, nid, rb, c, 3u, lmax);
         } else {
           // a letter extends the partial word: roll the word hash, probe the lexicon
           uint32_t nfl = 0, nwid = 0;
@@ -566,8 +740,10 @@ struct BeamDecoder {
               unsigned long long h = sm.whash[cur][rb];
               for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
               uint32_t lw, lf;
-              if (io.stats) atom_add(&io.stats[4], 1ULL);
-              if (lex_find(lm, h, lw, lf)) {
+              if (io.stats) atom_add(&sm.cnt[4], 1u);
+              bool lfound;
+              { CORAL_OP_T0(io.stats != nullptr); lfound = lex_find(lm, h, lw, lf); CORAL_OP_T1(io.stats != nullptr, sm, 3); }
+              if (lfound) {
                 nfl = ((lf & kLexPrefixOfUnigram) ? 0u : kOovPartial) | ((lf & kLexInUnigrams) ? kInUni : 0u) |
                       ((lf & kLexInLm) ? kInLm : 0u);
                 nwid = lw;
@@ -577,7 +753,7 @@ struct BeamDecoder {
             }
             ps = partial_score(P, wlen_m + P.label_ncp[c], nfl);
           }
-          emit(sm, outs, q, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
+          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
                2u | (nfl << 2), lmax);
         }
       }
@@ -589,7 +765,7 @@ struct BeamDecoder {
   // ---- overflow path: more candidates than the shared-memory arrays hold ------------------
   // Radix-select the beam_width best keys in HBM, then pull the winners into shared memory
   // so that phase 3 ranks them exactly like the common case. `thr` = prune threshold key.
-  static CORAL_DEV void select_overflow(Sm& sm, const DecodeParams& P, const OutView& g, int q,
+  static CORAL_DEV_OUTLINE void select_overflow(Sm& sm, const DecodeParams& P, const OutView& g, int q,
                                         unsigned long long thr) {
     const uint32_t n = sm.n_out[q];
     uint32_t* hist = reinterpret_cast<uint32_t*>(sm.o_key);  // 256 bins; o_key is unused until the pull
@@ -678,20 +854,61 @@ struct BeamDecoder {
 
   // ---- phase 3: prune, trim to beam_width, rank, write the next beam list -------------------
   // rank = number of candidates that beat this one under (score desc, first-candidate index
-  // asc) -- pyctcdecode's stable heapq.nlargest. Candidates below the prune threshold never
-  // beat a survivor, so the count runs over the dense key array without any filter.
+  // asc) -- pyctcdecode's stable heapq.nlargest. Candidates were dropped into kNB score
+  // buckets (monotone in the score) while they were produced, so
+  //   rank = (candidates in better buckets) + (bucket-mates that beat it):
+  // a counting sort by bucket, then comparisons inside the bucket only -- ~100 instructions
+  // per survivor instead of a pass over every candidate, exact for any score distribution.
+  // Candidates below the prune threshold never beat a survivor, so they need no filter.
+  static CORAL_DEV void rebucket(Sm& sm, const DecodeParams& P, int q) {  // overflow path only
+    const uint32_t n = sm.n_out[q];
+    const double scale = bucket_scale(P);
+    CORAL_LANES(NT) {
+      for (int i = lane; i < kNB; i += NT) sm.bcnt[i] = 0;
+      for (int i = lane; i < kNB / 8; i += NT) sm.gcnt[i] = 0;
+    }
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) {
+      for (uint32_t i = lane; i < n; i += NT) {
+        const uint32_t b = bucket_of(sm.mhat, scale, key_to_double(sm.o_key[i]));
+        sm.o_pos[i] = (uint16_t)atom_add(&sm.bcnt[b], 1u);
+        sm.o_bkt[i] = (uint8_t)b;
+        atom_add(&sm.gcnt[b >> 3], 1u);
+      }
+    }
+    CORAL_GSYNC(NT);
+  }
   static CORAL_DEV void rank_and_commit(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
-                                        int cur, int q, unsigned long long thr, bool final_pass) {
+                                        int cur, int q, unsigned long long thr, bool final_pass,
+                                        PhaseTimer* pt = nullptr) {
     const int nxt = cur ^ 1;
     const uint32_t n = sm.n_out[q];
     CORAL_LANES(NT) {
       if (!final_pass) clear_hash(sm, lane);
       for (uint32_t i = lane; i < n; i += NT) {
+        const uint32_t b = sm.o_bkt[i];
+        uint32_t base = 0;
+#pragma unroll 4
+        for (uint32_t g = 0; g < (b >> 3); ++g) base += sm.gcnt[g];
+#pragma unroll 4
+        for (uint32_t d = b & ~7u; d < b; ++d) base += sm.bcnt[d];
+        sm.o_sorted[base + sm.o_pos[i]] = (uint16_t)i;
+        sm.o_pos[i] = (uint16_t)base;  // from here on: first slot of its bucket
+      }
+    }
+    CORAL_GSYNC(NT);
+    if (pt) pt->mark(12);
+    CORAL_LANES(NT) {
+      for (uint32_t i = lane; i < n; i += NT) {
         const unsigned long long ki = sm.o_key[i];
         if (ki < thr) continue;
         const uint32_t oi = sm.o_order[i];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < n; ++j) {
+        const uint32_t base = sm.o_pos[i];
+        const uint32_t cnt = sm.bcnt[sm.o_bkt[i]];
+        uint32_t r = base;
+#pragma unroll 2
+        for (uint32_t m = 0; m < cnt; ++m) {
+          const uint32_t j = sm.o_sorted[base + m];
           const unsigned long long kj = sm.o_key[j];
           r += kj > ki;
           if (kj == ki) r += sm.o_order[j] < oi;
@@ -700,14 +917,7 @@ struct BeamDecoder {
         atom_add(&sm.S[q], 1u);
         const double logit = sm.o_logit[i];
         if (final_pass) {
-          double comb;
-          {
-            unsigned long long u = ki;
-            u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
-            union { double d; unsigned long long u; } cv;
-            cv.u = u;
-            comb = cv.d;
-          }
+          const double comb = key_to_double(ki);
           sm.logit[nxt][r] = logit;
           sm.lm_raw[nxt][r] = comb;        // final: combined score travels in lm_raw
           sm.node[nxt][r] = sm.o_child[i];  // final: text node
@@ -737,7 +947,7 @@ struct BeamDecoder {
             unsigned long long h = sm.whash[cur][rb];
             for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
             const uint32_t wl = (uint32_t)sm.wlen[cur][rb] + P.label_ncp[c];
-            sm.node[nxt][r] = trie_get_or_add(sm, sc, sm.node[cur][rb], c, 0u);
+            { CORAL_OP_T0(pt != nullptr && pt->stats != nullptr); sm.node[nxt][r] = trie_get_or_add(sm, sc, sm.node[cur][rb], c, 0u); CORAL_OP_T1(pt != nullptr && pt->stats != nullptr, sm, 4); }
             sm.bnd[nxt][r] = sm.bnd[cur][rb];
             sm.wid[nxt][r] = sm.o_aux[i];
             sm.whash[nxt][r] = h;
@@ -759,21 +969,21 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
+    if (pt) pt->mark(13);
   }
 
   static CORAL_DEV unsigned long long prune_key(Sm& sm, const DecodeParams& P, int q) {
     // max_score + beam_prune_logp in float64, back in key space
-    unsigned long long u = sm.gmax[q];
-    u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
-    union { double d; unsigned long long u; } c;
-    c.u = u;
-    return ordered_u64(d_add(c.d, P.beam_prune_logp));
+    return ordered_u64(d_add(key_to_double(sm.gmax[q]), P.beam_prune_logp));
   }
 
   // ---- one frame: 3 barriers on the common path ------------------------------------------------
   static CORAL_DEV void frame_step(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc,
                                    const UttIO& io, int f, int cur, int q, uint32_t nb) {
-    hash_beams(sm, cur, q, nb);
+    PhaseTimer pt;
+    pt.start(io.stats);
+    hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]]);
+    pt.mark(8);
     const uint32_t n_slots = sm.nN[q] * ((uint32_t)sm.nkept[f] + 1u);
     const bool in_smem = n_slots <= (uint32_t)OUTC;
     if (!in_smem && n_slots > sc.outs_cap) {
@@ -782,19 +992,26 @@ struct BeamDecoder {
       return;
     }
     const OutView outs = in_smem ? smem_outs(sm) : sc.outs_g;
-    expand(sm, lm, P, sc, io, f, cur, q, nb, outs);
+    expand(sm, lm, P, sc, io, f, cur, q, nb, outs, in_smem);
+    pt.mark(9);
     const unsigned long long thr = prune_key(sm, P, q);
-    if (!in_smem) select_overflow(sm, P, outs, q, thr);
-    rank_and_commit(sm, lm, P, sc, cur, q, thr, false);
+    if (!in_smem) {
+      select_overflow(sm, P, outs, q, thr);
+      rebucket(sm, P, q);
+      pt.mark(10);
+    }
+    rank_and_commit(sm, lm, P, sc, cur, q, thr, false, &pt);
     trie_maybe_grow(sm, sc, P, io);
+    pt.mark(14);
   }
 
   // ---- end of utterance ------------------------------------------------------
-  static CORAL_DEV uint32_t finalize(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+  static CORAL_DEV_OUTLINE uint32_t finalize(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
                                      const UttIO& io, int cur, int q, uint32_t nb) {
-    hash_beams(sm, cur, q, nb);
+    hash_beams(sm, cur, q, nb, 0.0);
     const uint32_t nN = sm.nN[q];
     const OutView outs = smem_outs(sm);  // nN <= beam_width <= OUTC
+    const double bscale = bucket_scale(P);
     CORAL_LANES(NT) {
       unsigned long long lmax = 0;
       for (uint32_t j = lane; j < nN; j += NT) {
@@ -827,12 +1044,12 @@ struct BeamDecoder {
           const bool oov = !open || (lm.has_unigrams && !(lfl & kInUni)) || !in_lm;
           LmState out;
           const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][last]].st, in_lm ? sm.wid[cur][last] : 0u, oov,
-                                          true, out, io.stats);
+                                          true, out, io.stats ? sm.cnt : nullptr);
           comb = d_add(logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
         }
         // text node: the open-word node itself, or the parent of a closed-word node
-        emit(sm, outs, q, comb, logit, first, 0u, open_or_root ? sm.node[cur][rb] : sm.parent[cur][rb], rb, 0u, 0u,
-             lmax);
+        emit(sm, outs, q, true, bscale, comb, logit, first, 0u, open_or_root ? sm.node[cur][rb] : sm.parent[cur][rb],
+             rb, 0u, 0u, lmax);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
@@ -844,7 +1061,12 @@ struct BeamDecoder {
       if (lane == 0) {
         *io.out_n = (int32_t)nf;
         *io.out_status = sm.status;
-        if (io.stats) { atom_add(&io.stats[5], (unsigned long long)sm.node_count); atom_add(&io.stats[6], (unsigned long long)sm.bnd_count); }
+        if (io.stats) {
+          sm.cnt[5] = sm.node_count;
+          sm.cnt[6] = sm.bnd_count;
+          for (int k = 0; k < 8; ++k) atom_add(&io.stats[k], (unsigned long long)sm.cnt[k]);
+          for (int k = 0; k < 8; ++k) { atom_add(&io.stats[16 + k], sm.opc[k]); atom_add(&io.stats[24 + k], (unsigned long long)sm.opn[k]); }
+        }
       }
       for (uint32_t r = lane; r < nf && r < (uint32_t)P.n_best; r += NT) {
         io.out_logit[r] = sm.logit[fin][r];
@@ -870,13 +1092,14 @@ struct BeamDecoder {
       clear_hash(sm, lane);
       if (lane == 0) {
         sm.status = 0;
+        for (int k = 0; k < 8; ++k) { sm.cnt[k] = 0; sm.opc[k] = 0; sm.opn[k] = 0; }
         sm.node_count = 1;
         sm.bnd_count = 1;
-        sm.ch_mask = (kChInit - 1u) < sc.ch_mask_max ? (kChInit - 1u) : sc.ch_mask_max;
         sm.nN[0] = sm.nN[1] = 0;
         sm.n_out[0] = sm.n_out[1] = 0;
         sm.S[0] = sm.S[1] = 0;
-        sm.gmax[0] = sm.gmax[1] = 0;
+        sm.gmax[0] = 0;
+        sm.gmax[1] = ordered_u64(0.0);  // "previous frame's best score" of the empty beam
         sm.logit[0][0] = 0.0;
         sm.lm_raw[0][0] = 0.0;
         sm.whash[0][0] = kWordHashSeed;
@@ -898,12 +1121,24 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
+    {
+      // child table: ~48 slots per frame keeps it under half full for typical utterances
+      uint32_t size = kChMin;
+      while (size < 48u * (uint32_t)io.T && size - 1u < sc.ch_mask_max) size <<= 1;
+      if (size - 1u > sc.ch_mask_max) size = sc.ch_mask_max + 1u;
+      trie_clear(sm, sc, size);
+    }
     int cur = 0, q = 0;
     uint32_t nb = 1;
     bool failed = false;
     for (int t0 = 0; t0 < io.T && !failed; t0 += kChunk) {
       const int nf = io.T - t0 < kChunk ? io.T - t0 : kChunk;
-      stage_frames(sm, P, io, t0, nf);
+      {
+        PhaseTimer ps;
+        ps.start(io.stats);
+        stage_frames(sm, P, io, t0, nf);
+        ps.mark(15);
+      }
       for (int f = 0; f < nf; ++f) {
         frame_step(sm, lm, P, sc, io, f, cur, q, nb);
         if (sm.status != 0) { failed = true; break; }

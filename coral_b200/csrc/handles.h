@@ -27,7 +27,6 @@ struct coral_decoder {
   size_t slot_bytes = 0;
   uint32_t n_slots = 0;
   uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0;
-  uint32_t* d_slot_epoch = nullptr;
   int32_t* d_work = nullptr;
   float* d_rowsum = nullptr;   // [B * T_max] for the probabilities-vs-logits detection
   int32_t* d_is_prob = nullptr;

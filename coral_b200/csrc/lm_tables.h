@@ -143,9 +143,24 @@ CORAL_HD float f32_add(float a, float b) {
 // Longest match found by extending the chain key one context word at a time and
 // stopping at the first absent n-gram; then the unused context back-offs are added
 // in float32 in ascending context length.
+// The chain keys depend only on the words, so on the device a first pass computes them and
+// prefetches every order's slot into L1; the second pass is the dependent chain, which then
+// hits L1 instead of paying one L2/HBM round trip per order. Loops are kept rolled: this
+// routine sits on the per-frame path of the beam kernel, whose code must stay cache-sized.
 CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, LmState& out,
                              int* probes = nullptr) {
   const UniEntry u = lm.uni[w];
+  const uint32_t nctx = in.len < (uint32_t)(lm.order - 1) ? in.len : (uint32_t)(lm.order > 0 ? lm.order - 1 : 0);
+#if defined(__CUDA_ARCH__)
+  {
+    uint64_t key = ng_key_push(kNgSeed, w);
+#pragma unroll 1
+    for (uint32_t i = 0; i < nctx; ++i) {
+      key = ng_key_push(key, in.w[i]);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(lm.ng + (key & lm.ng_mask)));
+    }
+  }
+#endif
   float prob = u.prob;
   out.w[0] = w;
   out.b[0] = u.backoff;
@@ -153,9 +168,9 @@ CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, Lm
   uint32_t ngram_len = 1;
   uint64_t key = ng_key_push(kNgSeed, w);
   int np = 1;
-  for (uint32_t i = 0; i < in.len; ++i) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < nctx; ++i) {
     const int n = (int)i + 2;
-    if (n > lm.order) break;
     key = ng_key_push(key, in.w[i]);
     float p, b;
     ++np;
@@ -168,6 +183,7 @@ CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, Lm
       ++olen;
     }
   }
+#pragma unroll 1
   for (uint32_t i = ngram_len - 1; i < in.len; ++i) prob = f32_add(prob, in.b[i]);
   const uint32_t keep = (uint32_t)(lm.order - 1);
   out.len = olen < keep ? olen : keep;

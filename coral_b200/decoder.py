@@ -189,7 +189,7 @@ class BeamSearchDecoderCTC:
             lengths = torch.tensor(list(lengths))
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         d_order = torch.argsort(d_len, descending=True).to(torch.int32)
-        d_stats = torch.zeros(8, dtype=torch.int64, device=dev) if collect_stats else None
+        d_stats = torch.zeros(32, dtype=torch.int64, device=dev) if collect_stats else None
         d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
             d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats)
         if not to_host:

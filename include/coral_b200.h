@@ -96,8 +96,10 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *   out_tokens      uint8 [B, n_best, T_max] alphabet indices of the text (no blanks)
  *   out_lens        int32 [B, n_best]
  *   out_status      int32 [B]           0 or CORAL_ECAP for that utterance
- *   stats_dev       uint64 [8] or NULL: beam extensions, LM word scorings, n-gram probes,
- *                   frames, lexicon probes (work counters of SURVEY 8d)
+ *   stats_dev       uint64 [32] or NULL: beam extensions, LM word scorings, n-gram probes,
+ *                   frames, lexicon probes, trie nodes, LM boundary records, child-table
+ *                   growths (work counters of SURVEY 8d); [8..15] = cycles per kernel phase,
+ *                   [16..23] / [24..31] = cycles / calls of selected device operations (tuning)
  * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
                               const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V,

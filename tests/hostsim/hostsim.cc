@@ -108,16 +108,15 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   while (chs < 2 * sc.node_cap) chs <<= 1;
   sc.ch_mask_max = chs - 1;
   sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 64);
-  std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap), ch_vals(chs);
-  std::vector<unsigned long long> ch_keys(chs, 0ULL);
+  std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap);
+  std::vector<unsigned long long> ch_tab(chs, 0x1234567812345678ULL);  // dirty: decode() must clear what it uses
   std::vector<BndRec> bnd(sc.bnd_cap);
   std::vector<unsigned long long> g_key(sc.outs_cap);
   std::vector<double> g_logit(sc.outs_cap);
   std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
   sc.node_parent = node_parent.data();
   sc.node_info = node_info.data();
-  sc.ch_keys = ch_keys.data();
-  sc.ch_vals = ch_vals.data();
+  sc.ch = ch_tab.data();
   sc.bnd = bnd.data();
   sc.outs_g.key = g_key.data();
   sc.outs_g.logit = g_logit.data();
@@ -125,11 +124,9 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   sc.outs_g.aux = g_aux.data();
   sc.outs_g.child = g_child.data();
   sc.outs_g.info = g_info.data();
-  sc.epoch = 0;
   int32_t status = 0;
   // decode the same utterance n_utt_repeat times on the same slot: exercises the epoch reuse
   for (int rep = 0; rep < n_utt_repeat; ++rep) {
-    sc.epoch += 1;
     UttIO io;
     io.logits = logits;
     io.T = T;

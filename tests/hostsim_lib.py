@@ -94,7 +94,7 @@ class HostSim:
         out_comb = np.zeros(n_best, np.float64)
         out_tok = np.zeros((n_best, Tm), np.uint8)
         out_len = np.zeros(n_best, np.int32)
-        stats = np.zeros(8, np.uint64)
+        stats = np.zeros(32, np.uint64)
         self.lib.hs_decode.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
             C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -33,3 +33,14 @@ frames = int(wl.lengths.sum())
 ms = float(np.median(ts))
 print(f"NT={os.environ.get('CORAL_BEAM_NT','default')} utts={a.utts} beam={a.beam} kind={a.kind}: {ms:.2f} ms  "
       f"{a.utts/ms*1e3:.0f} utt/s  {ms*1e3/frames*1e3:.1f} ns/frame-amortised  (min {min(ts):.2f})")
+if os.environ.get("CORAL_PHASES"):
+    out = dec.decode_padded(d_logits, d_len, beam_width=a.beam, n_best=1, input_mode=a.mode, collect_stats=True)
+    st = out.stats.astype(np.float64)
+    fr = st[3]
+    names = ["hash", "expand", "ovf-select", "bucket", "scatter", "rank+commit", "grow", "stage"]
+    tot = st[8:16].sum()
+    print("per-frame cycles (thread 0): " + ", ".join(f"{n}={st[8+i]/fr:.0f}" for i, n in enumerate(names)) + f"  total={tot/fr:.0f}")
+    ops = ["trie_find", "lm_word_score", "trie_add(expand)", "lex_find", "trie_add(commit)"]
+    print("op latency (cycles/call, calls/frame): " + ", ".join(
+        f"{n}={st[16+i]/max(st[24+i],1):.0f}x{st[24+i]/fr:.2f}" for i, n in enumerate(ops)))
+    print(f"per frame: ext={st[0]/fr:.1f} lm_scorings={st[1]/fr:.2f} ngram_probes={st[2]/fr:.2f} lex_probes={st[4]/fr:.2f} nodes={st[5]/fr:.2f} growths/utt={st[7]/a.utts:.2f}")
