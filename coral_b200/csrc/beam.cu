@@ -41,8 +41,9 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
   size_t o = 0;
   off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
   off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
-  off[2] = o; o = align16(o + (size_t)ch_size * 8);        // child table (key << 32 | id)
+  off[2] = o;                                              // (unused)
   off[3] = o;                                              // (unused)
+  (void)ch_size;
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
   off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
   off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
@@ -65,7 +66,6 @@ __global__ void __launch_bounds__(NT, (768 / NT) > 0 ? (768 / NT) : 1) beam_sear
     uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
     sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
     sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
-    sc.ch = reinterpret_cast<unsigned long long*>(base + off[2]);
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
     sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
     sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(NT, (768 / NT) > 0 ? (768 / NT) : 1) beam_sear
     sc.outs_g.info = sc.outs_g.child + L.outs_cap;
     sc.node_cap = L.node_cap;
     sc.bnd_cap = L.bnd_cap;
-    sc.ch_mask_max = L.ch_size - 1;
     sc.outs_cap = L.outs_cap;
   }
   for (;;) {
@@ -160,14 +159,13 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   if (per_sm < 1) return fail(CORAL_ECUDA, "beam kernel does not fit on an SM");
   const uint32_t want = (uint32_t)std::min<int64_t>((int64_t)B, (int64_t)per_sm * sm_count(dec->device));
 
-  // scratch: worst-case arenas per slot (every frame can add beam_width letter nodes and
-  // beam_width word-boundary nodes), bounded by a memory budget.
+  // scratch: worst-case arenas per slot (every frame can add beam_width back-pointer records
+  // and beam_width LM boundary records), bounded by a memory budget.
   const uint64_t T = (uint64_t)std::max(1, L.P.T_max);
   const uint64_t bw = (uint64_t)L.P.beam_width;
-  uint32_t node_cap = (uint32_t)std::min<uint64_t>(2 * bw * T + 64, (1u << 24) - 1);
+  uint32_t node_cap = (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu);
   uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
-  uint32_t ch_size = 64;
-  while (ch_size < 2 * node_cap) ch_size <<= 1;
+  uint32_t ch_size = 0;
   uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
   size_t off[7];
   const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);

@@ -155,10 +155,9 @@ struct OutView {
 struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after utterance
   uint32_t* node_parent;
   uint32_t* node_info;  // tok | bnd << 8
-  unsigned long long* ch;  // child table: node_key32(parent, tok) << 32 | node id ; 0 = empty
   BndRec* bnd;
   OutView outs_g;       // overflow for frames with more candidates than fit in smem
-  uint32_t node_cap, bnd_cap, ch_mask_max, outs_cap;
+  uint32_t node_cap, bnd_cap, outs_cap;
 };
 
 struct UttIO {
@@ -172,13 +171,12 @@ struct UttIO {
   uint8_t* out_tokens;  // [n_best, T_max]
   int32_t* out_len;     // [n_best]
   int32_t* out_status;  // scalar: 0 ok, -4 capacity
-  // optional [16]: extensions, LM scorings, n-gram probes, frames, lexicon probes, trie nodes,
-  // LM boundary records, child-table growths; [8..15] cycles per phase (thread 0): hash, expand,
+  // optional [16]: extensions, LM scorings, n-gram probes, frames, lexicon probes, back-pointer records,
+  // LM boundary records, (unused); [8..15] cycles per phase (thread 0): hash, expand,
   // overflow select, bucket, scatter, rank+commit, grow, frame staging
   unsigned long long* stats;
 };
 
-constexpr uint32_t kChMin = 1024;   // smallest child table; sized ~48 entries per frame, grows x4
 constexpr int kNB = 64;             // score buckets over the prune window
 
 template <int BW, int OUTC>
@@ -188,15 +186,15 @@ struct GroupShared {
   double logit[2][BW];
   double lm_raw[2][BW];
   unsigned long long whash[2][BW];
-  uint32_t node[2][BW];
-  uint32_t parent[2][BW];
-  uint32_t gparent[2][BW];
+  unsigned long long nh[2][BW];  // identity of the text prefix: 64-bit hash of its token string
+  unsigned long long ph[2][BW];  // identity of its parent prefix
+  uint32_t node[2][BW];          // back-pointer arena index (text output only)
   uint32_t bnd[2][BW];
   uint32_t wid[2][BW];
-  uint32_t meta[2][BW];  // tok | lc << 8 | flags << 16 | parent's tok << 24
+  uint32_t meta[2][BW];  // tok | lc << 8 | flags << 16
   uint16_t wlen[2][BW];
   // live-node hash
-  uint32_t hkey[HS];
+  unsigned long long hkey[HS];
   uint16_t sb0[HS], sb1[HS];
   uint16_t ne_slot[BW];
   // candidates of this frame (also reused as the 256-bin histogram of the overflow path)
@@ -223,7 +221,7 @@ struct GroupShared {
   double mhat;  // reference score of this frame's buckets: an estimate of its best score
   unsigned long long sel_prefix, sel_mask;
   uint32_t nN[2], n_out[2], S[2];
-  uint32_t node_count, bnd_count, ch_mask;
+  uint32_t node_count, bnd_count;
   uint32_t sel_need, sel_eq, sel_cut, sel_n;
   uint32_t gsum[16];
   int32_t status, utt;
@@ -232,19 +230,27 @@ struct GroupShared {
   uint32_t opn[8];            //         and how many times each ran
 };
 
-CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags, uint32_t ptok) {
-  return tok | (lc << 8) | (flags << 16) | (ptok << 24);
-}
+CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags) { return tok | (lc << 8) | (flags << 16); }
 CORAL_HD uint32_t meta_tok(uint32_t m) { return m & 0xFFu; }
 CORAL_HD uint32_t meta_lc(uint32_t m) { return (m >> 8) & 0xFFu; }
 CORAL_HD uint32_t meta_flags(uint32_t m) { return (m >> 16) & 0xFFu; }
-CORAL_HD uint32_t meta_ptok(uint32_t m) { return m >> 24; }
 constexpr uint32_t kLcNone = 0xFFu;   // last_char None (start of utterance)
 constexpr uint32_t kLcBlank = 0xFEu;  // last_char "" (blank)
 
-CORAL_HD uint32_t node_key(uint32_t parent, uint32_t tok) {
-  // (parent + 1) in 24 bits, token in 8: the root (kNoNode, kNoTok) maps to 0xFF and no key is 0
-  return (((parent + 1u) & 0xFFFFFFu) << 8) | tok;
+// Identity of a text prefix = 64-bit hash of its (space-normalised) token string, rolled one
+// token at a time. Two prefixes are "the same text" iff their hashes are equal -- the same
+// kind of guarantee KenLM gives for n-gram identity (64-bit hashes, no stored strings); with
+// ~1e4 prefixes per utterance the collision probability is ~3e-12 per utterance. This
+// replaces a per-utterance (parent, token) -> node table in HBM whose dependent
+// compare-and-swap round trips (~6k cycles each) dominated the frame time.
+constexpr unsigned long long kRootHash = 0x452821E638D01377ULL;
+CORAL_HD unsigned long long child_hash(unsigned long long h, uint32_t tok) {
+  // two multiply/xor-shift rounds: this hash IS the identity, so it gets the better mixing
+  h = (h ^ (0x9E3779B97F4A7C15ULL * (unsigned long long)(tok + 1u))) * 0xff51afd7ed558ccdULL;
+  h ^= h >> 33;
+  h *= 0xc4ceb9fe1a85ec53ULL;
+  h ^= h >> 29;
+  return h ? h : 1ULL;  // 0 marks an empty hash slot
 }
 
 // pyctcdecode LanguageModel.score_partial_token, hotwords empty
@@ -326,102 +332,35 @@ struct BeamDecoder {
   using Sm = GroupShared<BW, OUTC>;
   static constexpr int HS = Sm::HS;
 
-  // ---- live-node hash (shared memory) ------------------------------------------------
-  static CORAL_DEV uint32_t h_slot(uint32_t key) { return (key * 0x9E3779B1u) >> 7; }
-  static CORAL_DEV int h_find(Sm& sm, uint32_t key) {
-    uint32_t i = h_slot(key) & (HS - 1);
+  // ---- live-node hash (shared memory), keyed by the prefix hash ------------------------
+  static CORAL_DEV int h_find(Sm& sm, unsigned long long key) {
+    uint32_t i = (uint32_t)(key >> 20) & (HS - 1);
     for (;;) {
-      const uint32_t k = sm.hkey[i];
+      const unsigned long long k = sm.hkey[i];
       if (k == key) return (int)i;
       if (k == 0) return -1;
       i = (i + 1) & (HS - 1);
     }
   }
   // returns the slot; `created` tells the caller it is the one that inserted the key
-  static CORAL_DEV int h_insert(Sm& sm, uint32_t key, bool& created) {
-    uint32_t i = h_slot(key) & (HS - 1);
+  static CORAL_DEV int h_insert(Sm& sm, unsigned long long key, bool& created) {
+    uint32_t i = (uint32_t)(key >> 20) & (HS - 1);
     for (;;) {
-      const uint32_t k = atom_cas_u32(&sm.hkey[i], 0u, key);
+      const unsigned long long k = atom_cas_u64(&sm.hkey[i], 0ULL, key);
       if (k == 0) { created = true; return (int)i; }
       if (k == key) { created = false; return (int)i; }
       i = (i + 1) & (HS - 1);
     }
   }
 
-  // ---- per-utterance trie child table (HBM) ------------------------------------------
-  // One 64-bit word per slot, key in the high half and node id in the low half, cleared at
-  // the start of the utterance: a lookup is one load and an insert is one compare-and-swap
-  // with no prior load (the dependent round trips to HBM/L2 are the critical path here).
-  static CORAL_DEV uint32_t ch_slot(uint32_t key) { return (uint32_t)mix64(key); }
-  // Returns the node id of (parent, tok), creating it if absent.
-  static CORAL_DEV_OUTLINE uint32_t trie_get_or_add(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok,
-                                                    uint32_t bnd) {
-    const uint32_t key = node_key(parent, tok);
+  // ---- back-pointer arena (HBM): append-only (parent index, token) records used only to
+  // write out the winning transcripts; duplicates of a prefix are harmless here.
+  static CORAL_DEV uint32_t arena_append(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok) {
     const uint32_t id = atom_add(&sm.node_count, 1u);
     if (id >= sc.node_cap) { sm.status = -4; return 0; }
-    const unsigned long long mine = ((unsigned long long)key << 32) | id;
-    uint32_t i = ch_slot(key) & sm.ch_mask;
-    for (;;) {
-      const unsigned long long old = atom_cas_u64(&sc.ch[i], 0ULL, mine);
-      if (old == 0) {
-        sc.node_parent[id] = parent;
-        sc.node_info[id] = tok | (bnd << 8);
-        return id;
-      }
-      if ((uint32_t)(old >> 32) == key) {  // already there: the fresh id stays unused (marked so a
-        sc.node_parent[id] = kNoNode;      // later table growth skips it)
-        sc.node_info[id] = kNoTok;
-        return (uint32_t)old;
-      }
-      i = (i + 1) & sm.ch_mask;
-    }
-  }
-  static CORAL_DEV_OUTLINE bool trie_find(Sm& sm, const SlotScratch& sc, uint32_t parent, uint32_t tok, uint32_t& id) {
-    const uint32_t key = node_key(parent, tok);
-    uint32_t i = ch_slot(key) & sm.ch_mask;
-    for (;;) {
-      const unsigned long long w = sc.ch[i];
-      if (w == 0) return false;
-      if ((uint32_t)(w >> 32) == key) { id = (uint32_t)w; return true; }
-      i = (i + 1) & sm.ch_mask;
-    }
-  }
-  static CORAL_DEV void trie_clear(Sm& sm, const SlotScratch& sc, uint32_t size) {
-    CORAL_LANES(NT) {
-#pragma unroll 2
-      for (uint32_t i = lane; i < size; i += NT) sc.ch[i] = 0ULL;
-      if (lane == 0) sm.ch_mask = size - 1u;
-    }
-    CORAL_GSYNC(NT);
-  }
-  // Keep the child table at most half full: grow x4 and re-insert every node.
-  static CORAL_DEV void trie_maybe_grow(Sm& sm, SlotScratch& sc, const DecodeParams& P, const UttIO& io) {
-    const uint32_t need = (sm.node_count + 2u * (uint32_t)P.beam_width + 2u) * 2u;
-    if (need <= sm.ch_mask + 1u || sm.ch_mask >= sc.ch_mask_max) return;  // uniform: read after a barrier
-    trie_grow(sm, sc, io, need);
-  }
-  static CORAL_DEV_OUTLINE void trie_grow(Sm& sm, SlotScratch& sc, const UttIO& io, uint32_t need) {
-    uint32_t size = sm.ch_mask + 1u;
-    while (size < need && size - 1u < sc.ch_mask_max) size <<= 2;
-    if (size - 1u > sc.ch_mask_max) size = sc.ch_mask_max + 1u;
-    CORAL_GSYNC(NT);
-    CORAL_LANES(NT) { if (lane == 0 && io.stats) sm.cnt[7] += 1u; }
-    trie_clear(sm, sc, size);
-    const uint32_t n = sm.node_count;
-    CORAL_LANES(NT) {
-      for (uint32_t id = 1 + lane; id < n; id += NT) {
-        if (sc.node_parent[id] == kNoNode) continue;  // unused id
-        const uint32_t key = node_key(sc.node_parent[id], sc.node_info[id] & 0xFFu);
-        const unsigned long long mine = ((unsigned long long)key << 32) | id;
-        uint32_t i = ch_slot(key) & sm.ch_mask;
-        for (;;) {
-          const unsigned long long old = atom_cas_u64(&sc.ch[i], 0ULL, mine);
-          if (old == 0 || (uint32_t)(old >> 32) == key) break;
-          i = (i + 1) & sm.ch_mask;
-        }
-      }
-    }
-    CORAL_GSYNC(NT);
+    sc.node_parent[id] = parent;
+    sc.node_info[id] = tok;
+    return id;
   }
 
   // ---- frame staging: log-softmax in float32 the way numpy evaluates it ---------------
@@ -433,6 +372,16 @@ struct BeamDecoder {
     CORAL_LANES(NT) {
 #pragma unroll 2
       for (int i = lane; i < nf * V; i += NT) sm.lp[i / V][i % V] = io.logits[(size_t)t0 * V + i];
+#if defined(__CUDA_ARCH__)
+      // pull the next chunk of this utterance towards L2 while this one is decoded
+      const int nxt0 = t0 + kChunk;
+      if (nxt0 < io.T) {
+        const int nn = (io.T - nxt0 < kChunk ? io.T - nxt0 : kChunk) * V;
+        const char* base = reinterpret_cast<const char*>(io.logits + (size_t)nxt0 * V);
+        for (int off = lane * 128; off < nn * 4; off += NT * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+#endif
     }
     CORAL_GSYNC(NT);
     const float lo = -34.538776f;  // float32(log(1e-15))
@@ -467,6 +416,7 @@ struct BeamDecoder {
       // eight lanes per frame: lane j owns numpy's accumulator r[j] (elements j, j+8, ...)
       float* pmax = reinterpret_cast<float*>(sm.o_logit);  // [kChunk][8], candidate arrays are idle here
       float* racc = pmax + kChunk * 8;                     // [kChunk][8]
+      float* erem = racc + kChunk * 8;                     // [kChunk][8] exp of the V % 8 tail elements
       const int main_n = V - (V % 8);
       CORAL_LANES(NT) {
         for (int p = lane; p < nf * 8; p += NT) {
@@ -492,7 +442,10 @@ struct BeamDecoder {
 #pragma unroll 1
           for (int i = j + 8; i < main_n; i += 8) { row[i] = f32_add(row[i], -mx); r = f32_add(r, expf(row[i])); }
           racc[p] = r;
-          if (main_n + j < V) row[main_n + j] = f32_add(row[main_n + j], -mx);  // remainder: summed in order below
+          if (main_n + j < V) {  // remainder: summed in order below
+            row[main_n + j] = f32_add(row[main_n + j], -mx);
+            erem[p] = expf(row[main_n + j]);
+          }
         }
       }
       CORAL_GSYNC(NT);
@@ -504,20 +457,8 @@ struct BeamDecoder {
           float s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])),
                             f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
 #pragma unroll 1
-          for (int i = main_n; i < V; ++i) s = f32_add(s, expf(row[i]));
-          const float ls = logf(s);
-          // every lane of the frame computed the same ls; each clips its own elements, but only
-          // after all eight have read the remainder values -> written in the next phase
-          pmax[p] = ls;
-          (void)j;
-        }
-      }
-      CORAL_GSYNC(NT);
-      CORAL_LANES(NT) {
-        for (int p = lane; p < nf * 8; p += NT) {
-          const int f = p >> 3, j = p & 7;
-          float* row = sm.lp[f];
-          const float ls = pmax[p];
+          for (int i = main_n; i < V; ++i) s = f32_add(s, erem[f * 8 + (i - main_n)]);
+          const float ls = logf(s);  // the same value in all eight lanes of the frame
 #pragma unroll 1
           for (int i = j; i < V; i += 8) {
             const float y = f32_add(row[i], -ls);
@@ -618,7 +559,7 @@ struct BeamDecoder {
       for (uint32_t b = lane; b < nb; b += NT) {
         const uint32_t mt = sm.meta[cur][b];
         bool created;
-        const int s = h_insert(sm, node_key(sm.parent[cur][b], meta_tok(mt)), created);
+        const int s = h_insert(sm, sm.nh[cur][b], created);
         if (created) sm.ne_slot[atom_add(&sm.nN[q], 1u)] = (uint16_t)s;
         if (meta_lc(mt) == kLcBlank) sm.sb0[s] = (uint16_t)b; else sm.sb1[s] = (uint16_t)b;
       }
@@ -661,7 +602,7 @@ struct BeamDecoder {
           // repeat of the node's own last token (or a space on a closed word): the text does
           // not change. If the parent node is live, its (parent, c) item gathers these beams.
           const uint32_t c = tok_m == kNoTok ? (uint32_t)P.space_id : tok_m;
-          if (tok_m != kNoTok && h_find(sm, node_key(sm.gparent[cur][rb], meta_ptok(mt))) >= 0) continue;
+          if (tok_m != kNoTok && h_find(sm, sm.ph[cur][rb]) >= 0) continue;
           int k = -1;
           for (int kk = 0; kk < K; ++kk) if (sm.kept[f][kk] == c) k = kk;
           if (k < 0) continue;
@@ -687,7 +628,7 @@ struct BeamDecoder {
         if ((int)c == P.space_id && wlen_m == 0) continue;  // a space after a closed word never extends
         if (b0 != kNone16) mem[nm++] = b0;
         if (b1 != kNone16 && tok_m != c) mem[nm++] = b1;
-        const int cs = h_find(sm, node_key(sm.node[cur][rb], c));
+        const int cs = h_find(sm, child_hash(sm.nh[cur][rb], c));
         if (cs >= 0) {
           if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
           if ((int)c == P.space_id && sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
@@ -702,33 +643,25 @@ struct BeamDecoder {
                                   partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])))),
                logit, order, 0u, crb, rb, c, 1u, lmax);
         } else if ((int)c == P.space_id) {
-          // a word closes: the boundary node is materialised at once (it carries the LM
-          // record, like pyctcdecode's cached_lm_scores entry for the new text)
-          uint32_t nid = 0, bnd_new = 0;
+          // a word closes: score it with the LM and keep the result in a boundary record
+          // (what pyctcdecode caches under the new text in cached_lm_scores)
+          uint32_t bnd_new = 0;
           double raw_new = sm.lm_raw[cur][rb];
-          bool have;
-          { CORAL_OP_T0(io.stats != nullptr); have = trie_find(sm, sc, sm.node[cur][rb], c, nid); CORAL_OP_T1(io.stats != nullptr, sm, 0); }
-          if (have) {
-            bnd_new = sc.node_info[nid] >> 8;
-            if (lm.present) raw_new = sc.bnd[bnd_new].lm_raw;
-          } else {
-            if (lm.present) {
-              bnd_new = atom_add(&sm.bnd_count, 1u);
-              if (bnd_new >= sc.bnd_cap) { sm.status = -4; bnd_new = 0; }
-              const bool in_lm = (fl_m & kInLm) != 0;
-              const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
-              BndRec nr;
-              CORAL_OP_T0(io.stats != nullptr);
-              const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u, oov,
-                                              false, nr.st, io.stats ? sm.cnt : nullptr);
-              CORAL_OP_T1(io.stats != nullptr, sm, 1);
-              nr.lm_raw = d_add(sm.lm_raw[cur][rb], sw);
-              raw_new = nr.lm_raw;
-              sc.bnd[bnd_new] = nr;
-            }
-            { CORAL_OP_T0(io.stats != nullptr); nid = trie_get_or_add(sm, sc, sm.node[cur][rb], c, bnd_new); CORAL_OP_T1(io.stats != nullptr, sm, 2); }
+          if (lm.present) {
+            bnd_new = atom_add(&sm.bnd_count, 1u);
+            if (bnd_new >= sc.bnd_cap) { sm.status = -4; bnd_new = 0; }
+            const bool in_lm = (fl_m & kInLm) != 0;
+            const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
+            BndRec nr;
+            CORAL_OP_T0(io.stats != nullptr);
+            const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u, oov,
+                                            false, nr.st, io.stats ? sm.cnt : nullptr);
+            CORAL_OP_T1(io.stats != nullptr, sm, 1);
+            nr.lm_raw = d_add(sm.lm_raw[cur][rb], sw);
+            raw_new = nr.lm_raw;
+            sc.bnd[bnd_new] = nr;
           }
-          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, nid, rb, c, 3u, lmax);
+          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, 0u, rb, c, 3u, lmax);
         } else {
           // a letter extends the partial word: roll the word hash, probe the lexicon
           uint32_t nfl = 0, nwid = 0;
@@ -931,38 +864,37 @@ struct BeamDecoder {
           const uint32_t src = kind == 0 ? rb : sm.o_child[i];
           const uint32_t mt = sm.meta[cur][src];
           sm.node[nxt][r] = sm.node[cur][src];
-          sm.parent[nxt][r] = sm.parent[cur][src];
-          sm.gparent[nxt][r] = sm.gparent[cur][src];
+          sm.nh[nxt][r] = sm.nh[cur][src];
+          sm.ph[nxt][r] = sm.ph[cur][src];
           sm.bnd[nxt][r] = sm.bnd[cur][src];
           sm.wid[nxt][r] = sm.wid[cur][src];
           sm.whash[nxt][r] = sm.whash[cur][src];
           sm.lm_raw[nxt][r] = sm.lm_raw[cur][src];
           sm.wlen[nxt][r] = sm.wlen[cur][src];
-          sm.meta[nxt][r] = meta_pack(meta_tok(mt), lc, meta_flags(mt), meta_ptok(mt));
+          sm.meta[nxt][r] = meta_pack(meta_tok(mt), lc, meta_flags(mt));
         } else {
-          const uint32_t pm = sm.meta[cur][rb];
-          sm.parent[nxt][r] = sm.node[cur][rb];
-          sm.gparent[nxt][r] = sm.parent[cur][rb];
+          // a new prefix: append its back-pointer (stores only, nothing waits on HBM here)
+          sm.node[nxt][r] = arena_append(sm, sc, sm.node[cur][rb], c);
+          sm.nh[nxt][r] = child_hash(sm.nh[cur][rb], c);
+          sm.ph[nxt][r] = sm.nh[cur][rb];
           if (kind == 2) {
             unsigned long long h = sm.whash[cur][rb];
             for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
             const uint32_t wl = (uint32_t)sm.wlen[cur][rb] + P.label_ncp[c];
-            { CORAL_OP_T0(pt != nullptr && pt->stats != nullptr); sm.node[nxt][r] = trie_get_or_add(sm, sc, sm.node[cur][rb], c, 0u); CORAL_OP_T1(pt != nullptr && pt->stats != nullptr, sm, 4); }
             sm.bnd[nxt][r] = sm.bnd[cur][rb];
             sm.wid[nxt][r] = sm.o_aux[i];
             sm.whash[nxt][r] = h;
             sm.lm_raw[nxt][r] = sm.lm_raw[cur][rb];
             sm.wlen[nxt][r] = (uint16_t)(wl > 65535u ? 65535u : wl);
-            sm.meta[nxt][r] = meta_pack(c, lc, kf >> 2, meta_tok(pm));
+            sm.meta[nxt][r] = meta_pack(c, lc, kf >> 2);
           } else {
             const uint32_t bn = sm.o_aux[i];
-            sm.node[nxt][r] = sm.o_child[i];
             sm.bnd[nxt][r] = bn;
             sm.wid[nxt][r] = 0;
             sm.whash[nxt][r] = kWordHashSeed;
             sm.lm_raw[nxt][r] = lm.present ? sc.bnd[bn].lm_raw : 0.0;
             sm.wlen[nxt][r] = 0;
-            sm.meta[nxt][r] = meta_pack(c, lc, 0u, meta_tok(pm));
+            sm.meta[nxt][r] = meta_pack(c, lc, 0u);
           }
         }
         sm.logit[nxt][r] = logit;
@@ -1001,8 +933,6 @@ struct BeamDecoder {
       pt.mark(10);
     }
     rank_and_commit(sm, lm, P, sc, cur, q, thr, false, &pt);
-    trie_maybe_grow(sm, sc, P, io);
-    pt.mark(14);
   }
 
   // ---- end of utterance ------------------------------------------------------
@@ -1020,13 +950,13 @@ struct BeamDecoder {
         const uint32_t mt = sm.meta[cur][rb];
         const bool open_or_root = sm.wlen[cur][rb] > 0 || meta_tok(mt) == kNoTok;
         // a closed-word node whose (open-word) parent is live is absorbed by the parent's group
-        if (!open_or_root && h_find(sm, node_key(sm.gparent[cur][rb], meta_ptok(mt))) >= 0) continue;
+        if (!open_or_root && h_find(sm, sm.ph[cur][rb]) >= 0) continue;
         uint32_t mem[4];
         int nm = 0;
         if (sm.sb0[s] != kNone16) mem[nm++] = sm.sb0[s];
         if (sm.sb1[s] != kNone16) mem[nm++] = sm.sb1[s];
         if (sm.wlen[cur][rb] > 0) {
-          const int cs = h_find(sm, node_key(sm.node[cur][rb], (uint32_t)P.space_id));
+          const int cs = h_find(sm, child_hash(sm.nh[cur][rb], (uint32_t)P.space_id));
           if (cs >= 0) {
             if (sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
             if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
@@ -1048,8 +978,8 @@ struct BeamDecoder {
           comb = d_add(logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
         }
         // text node: the open-word node itself, or the parent of a closed-word node
-        emit(sm, outs, q, true, bscale, comb, logit, first, 0u, open_or_root ? sm.node[cur][rb] : sm.parent[cur][rb],
-             rb, 0u, 0u, lmax);
+        emit(sm, outs, q, true, bscale, comb, logit, first, 0u,
+             open_or_root ? sm.node[cur][rb] : sc.node_parent[sm.node[cur][rb]], rb, 0u, 0u, lmax);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
@@ -1104,12 +1034,12 @@ struct BeamDecoder {
         sm.lm_raw[0][0] = 0.0;
         sm.whash[0][0] = kWordHashSeed;
         sm.node[0][0] = 0;
-        sm.parent[0][0] = kNoNode;
-        sm.gparent[0][0] = kNoNode;
+        sm.nh[0][0] = kRootHash;
+        sm.ph[0][0] = 0;
         sm.bnd[0][0] = 0;
         sm.wid[0][0] = 0;
         sm.wlen[0][0] = 0;
-        sm.meta[0][0] = meta_pack(kNoTok, kLcNone, 0u, kNoTok);
+        sm.meta[0][0] = meta_pack(kNoTok, kLcNone, 0u);
         sc.node_parent[0] = kNoNode;
         sc.node_info[0] = kNoTok;
         if (lm.present) {
@@ -1121,13 +1051,6 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
-    {
-      // child table: ~48 slots per frame keeps it under half full for typical utterances
-      uint32_t size = kChMin;
-      while (size < 48u * (uint32_t)io.T && size - 1u < sc.ch_mask_max) size <<= 1;
-      if (size - 1u > sc.ch_mask_max) size = sc.ch_mask_max + 1u;
-      trie_clear(sm, sc, size);
-    }
     int cur = 0, q = 0;
     uint32_t nb = 1;
     bool failed = false;

@@ -185,7 +185,7 @@ int load_arpa(const char* path, HostLm& lm, std::string& err) {
     lm.ng.assign(cap, NgSlot{0, 0.0f, 0.0f});
     lm.ng_mask = cap - 1;
     for (const auto& p : pending) {
-      uint64_t i = p.key & lm.ng_mask;
+      uint64_t i = (p.key >> 20) & lm.ng_mask;
       for (;;) {
         if (lm.ng[i].key == 0) { lm.ng[i] = NgSlot{p.key, p.prob, p.backoff}; break; }
         if (lm.ng[i].key == p.key) {
@@ -252,7 +252,7 @@ int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams,
   out.lex.assign(cap, LexSlot{0, 0, 0});
   out.lex_mask = cap - 1;
   for (const auto& kv : map) {
-    uint64_t i = kv.first & out.lex_mask;
+    uint64_t i = (kv.first >> 20) & out.lex_mask;
     while (out.lex[i].key != 0) i = (i + 1) & out.lex_mask;
     out.lex[i] = LexSlot{kv.first, kv.second.wid, kv.second.flags};
   }

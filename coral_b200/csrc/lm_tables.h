@@ -86,18 +86,19 @@ constexpr uint64_t kWordHashSeed = 0x243F6A8885A308D3ULL;
 constexpr uint64_t kNgSeed = 0x13198A2E03707344ULL;
 
 // rolling hash of a word, one Unicode code point at a time
-CORAL_HD uint64_t word_hash_push(uint64_t h, uint32_t cp) {
-  h = mix64(h ^ ((uint64_t)cp + 0x9E3779B97F4A7C15ULL));
+// Incremental hashes sit on dependent chains of the beam kernel's critical path, so each
+// step is one 64-bit multiply and one xor-shift (not a full finaliser); the builder checks
+// that no two distinct words / n-grams collide.
+CORAL_HD uint64_t hash_step(uint64_t h, uint64_t x) {
+  h = (h ^ (x + 0x9E3779B97F4A7C15ULL)) * 0xff51afd7ed558ccdULL;
+  h ^= h >> 32;
   return h ? h : 1;  // 0 is the empty-slot marker
 }
-
-CORAL_HD uint64_t ng_key_push(uint64_t k, uint32_t w) {
-  k = mix64(k * 0x9E3779B97F4A7C15ULL + (uint64_t)w + 1);
-  return k ? k : 1;
-}
+CORAL_HD uint64_t word_hash_push(uint64_t h, uint32_t cp) { return hash_step(h, (uint64_t)cp); }
+CORAL_HD uint64_t ng_key_push(uint64_t k, uint32_t w) { return hash_step(k, (uint64_t)w); }
 
 CORAL_HD bool lex_find(const LmView& lm, uint64_t h, uint32_t& wid, uint32_t& flags) {
-  uint64_t i = h & lm.lex_mask;
+  uint64_t i = (h >> 20) & lm.lex_mask;
   for (;;) {
 #if defined(__CUDA_ARCH__)
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(lm.lex + i));
@@ -114,7 +115,7 @@ CORAL_HD bool lex_find(const LmView& lm, uint64_t h, uint32_t& wid, uint32_t& fl
 }
 
 CORAL_HD bool ng_find(const LmView& lm, uint64_t k, float& prob, float& backoff) {
-  uint64_t i = k & lm.ng_mask;
+  uint64_t i = (k >> 20) & lm.ng_mask;
   for (;;) {
 #if defined(__CUDA_ARCH__)
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(lm.ng + i));
@@ -143,24 +144,24 @@ CORAL_HD float f32_add(float a, float b) {
 // Longest match found by extending the chain key one context word at a time and
 // stopping at the first absent n-gram; then the unused context back-offs are added
 // in float32 in ascending context length.
-// The chain keys depend only on the words, so on the device a first pass computes them and
-// prefetches every order's slot into L1; the second pass is the dependent chain, which then
-// hits L1 instead of paying one L2/HBM round trip per order. Loops are kept rolled: this
-// routine sits on the per-frame path of the beam kernel, whose code must stay cache-sized.
+// The chain keys depend only on the words, so the device path first prefetches every order's
+// slot into L1 and then walks the dependent chain against L1. Loops are kept rolled: this routine sits
+// on the per-frame path of the beam kernel, whose code must stay instruction-cache sized.
 CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, LmState& out,
                              int* probes = nullptr) {
-  const UniEntry u = lm.uni[w];
   const uint32_t nctx = in.len < (uint32_t)(lm.order - 1) ? in.len : (uint32_t)(lm.order > 0 ? lm.order - 1 : 0);
 #if defined(__CUDA_ARCH__)
   {
-    uint64_t key = ng_key_push(kNgSeed, w);
+    // first pass: every order's slot is prefetched into L1 (the keys depend only on the words)
+    uint64_t kp = ng_key_push(kNgSeed, w);
 #pragma unroll 1
     for (uint32_t i = 0; i < nctx; ++i) {
-      key = ng_key_push(key, in.w[i]);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(lm.ng + (key & lm.ng_mask)));
+      kp = ng_key_push(kp, in.w[i]);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(lm.ng + ((kp >> 20) & lm.ng_mask)));
     }
   }
 #endif
+  const UniEntry u = lm.uni[w];
   float prob = u.prob;
   out.w[0] = w;
   out.b[0] = u.backoff;

@@ -102,21 +102,16 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   memset(&lm, 0, sizeof(lm));
   if (d->has_lm) lm = make_view(d->lm, d->lx, d->lm.uni.data(), d->lm.ng.data(), d->lx.lex.data());
   SlotScratch sc;
-  sc.node_cap = (uint32_t)(2 * (size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
+  sc.node_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
   sc.bnd_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
-  uint32_t chs = 64;
-  while (chs < 2 * sc.node_cap) chs <<= 1;
-  sc.ch_mask_max = chs - 1;
   sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 64);
   std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap);
-  std::vector<unsigned long long> ch_tab(chs, 0x1234567812345678ULL);  // dirty: decode() must clear what it uses
   std::vector<BndRec> bnd(sc.bnd_cap);
   std::vector<unsigned long long> g_key(sc.outs_cap);
   std::vector<double> g_logit(sc.outs_cap);
   std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
   sc.node_parent = node_parent.data();
   sc.node_info = node_info.data();
-  sc.ch = ch_tab.data();
   sc.bnd = bnd.data();
   sc.outs_g.key = g_key.data();
   sc.outs_g.logit = g_logit.data();

@@ -1,7 +1,7 @@
 """CPU check of the beam-search KERNEL LOGIC (coral_b200/csrc/beam_core.h compiled with
 -DCORAL_HOSTSIM, lanes run sequentially) against the oracle. This validates the device
-algorithm -- node trie, gather-merge, LM records, prune/trim/rank, overflow path, child-table
-growth -- without a GPU; the `-m gpu` tests then check the real kernel through the C ABI."""
+algorithm -- prefix identity, gather-merge, LM records, prune/trim/rank, overflow path --
+without a GPU; the `-m gpu` tests then check the real kernel through the C ABI."""
 
 from __future__ import annotations
 
@@ -80,13 +80,13 @@ def test_flat_logits_overflow_and_trim(sim, oracle_decoder, rng):
     _check(oracle_decoder, sim, flat[:30], beam_width=300, token_min_logp=-3.0, variant=2)
 
 
-def test_child_table_growth(sim, oracle_decoder, rng):
-    """Enough new prefixes per utterance to outgrow the initial 4096-entry child table."""
+def test_long_flat_utterance_many_prefixes(sim, oracle_decoder, rng):
+    """Thousands of distinct prefixes in one utterance (back-pointer arena, slot reuse)."""
     from coral_b200 import synth
 
     lg = synth.flat_logits(120, rng)
     _check(oracle_decoder, sim, lg, beam_width=100, repeat=2)
-    assert sim.last_stats[7] >= 1 and sim.last_stats[5] > 2048
+    assert sim.last_stats[5] > 2048
 
 
 def test_edge_cases(sim, oracle_decoder, small_workload):
@@ -134,7 +134,9 @@ def test_probability_inputs(sim, oracle_decoder, small_workload):
 
 def test_work_counters_match_oracle(sim, oracle_decoder, small_workload):
     """Device-side work counters agree with the oracle's: beam extensions and
-    frames exactly; LM word scorings = the oracle's cached_lm_scores misses."""
+    frames exactly. LM word scorings are >= the oracle's cached_lm_scores misses: the device
+    re-scores a completed word whose text was scored before but is no longer on any beam
+    (same value, no text-keyed cache to consult)."""
     w = small_workload
     lg = w.logits[4, : w.lengths[4]]
     s0 = dict(oracle_decoder.stats)
@@ -143,4 +145,4 @@ def test_work_counters_match_oracle(sim, oracle_decoder, small_workload):
     sim.decode_beams(lg)
     st = sim.last_stats
     assert int(st[0]) == d["extensions"] and int(st[3]) == d["frames"]
-    assert int(st[1]) == d["n_score"]
+    assert d["n_score"] <= int(st[1]) <= 2 * d["n_score"]
