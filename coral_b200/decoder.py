@@ -37,6 +37,7 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 MAX_BEAM_WIDTH = 512
+H2D_CHUNK = 1024  # utterances per host->device chunk when the logits arrive from the host
 
 
 def _torch():
@@ -182,16 +183,38 @@ class BeamSearchDecoderCTC:
         if not 1 <= beam_width <= MAX_BEAM_WIDTH:
             raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
         n_best = max(1, min(int(n_best), int(beam_width)))
-        d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         if isinstance(lengths, np.ndarray):
             lengths = torch.from_numpy(np.ascontiguousarray(lengths))
         elif not torch.is_tensor(lengths):
             lengths = torch.tensor(list(lengths))
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
-        d_order = torch.argsort(d_len, descending=True).to(torch.int32)
         d_stats = torch.zeros(32, dtype=torch.int64, device=dev) if collect_stats else None
-        d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
-            d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats)
+        B = logits.shape[0]
+        if logits.device.type == "cpu" and B > 2 * H2D_CHUNK and logits.dtype == torch.float32:
+            # host logits: stream them in chunks on a copy stream so that the H2D transfer of
+            # chunk k+1 overlaps the decode of chunk k (pinned memory makes the copies async)
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            parts = []
+            for a0 in range(0, B, H2D_CHUNK):
+                b0 = min(B, a0 + H2D_CHUNK)
+                with torch.cuda.stream(self._copy_stream):
+                    d_chunk = logits[a0:b0].to(device=dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                d_chunk.record_stream(main)
+                main.wait_event(ev)
+                cl = d_len[a0:b0]
+                order = torch.argsort(cl, descending=True).to(torch.int32)
+                parts.append(self.decode_launch(d_chunk, cl, order, beam_width, beam_prune_logp, token_min_logp,
+                                                n_best, input_mode, d_stats))
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status = (torch.cat([p[k] for p in parts]) for k in range(6))
+        else:
+            d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
+                d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats)
         if not to_host:
             return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats
         out = DecodedBatch(d_n.cpu().numpy(), d_logit.cpu().numpy(), d_comb.cpu().numpy(), d_tok.cpu().numpy(),

@@ -328,3 +328,85 @@ def test_full_size_properties(gpu_decoder, torch_cuda, cache_dir, rng):
     full = gpu_decoder.decode_padded(w.logits[:32], w.lengths[:32], n_best=100)
     assert np.array_equal(full.lm_score[:, 0], a.lm_score[:32, 0])
     assert (np.diff(full.lm_score, axis=1)[np.arange(100)[None, 1:] < full.n_beams[:, None]] <= 0).all()
+
+
+# ------------------------------------------------------------------- golden fixtures on GPU
+def _golden(name):
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name), encoding="utf-8") as f:
+        return json.load(f)
+
+
+def test_golden_greedy_vectors_from_real_hf_tokenizer(torch_cuda, coral_vocab):
+    """ids -> strings through the CUDA collapse kernel == the real Wav2Vec2CTCTokenizer."""
+    from coral_b200.greedy import decode_ids
+
+    cases = [c for c in _golden("greedy_hf.json") if "ids" in c and len(c["ids"]) > 0]
+    T = max(len(c["ids"]) for c in cases)
+    ids = np.full((len(cases), T), 45, dtype=np.int32)
+    lens = np.array([len(c["ids"]) for c in cases], dtype=np.int32)
+    for i, c in enumerate(cases):
+        ids[i, : lens[i]] = c["ids"]
+    assert decode_ids(ids, coral_vocab, lengths=lens, group_tokens=True) == [c["grouped"] for c in cases]
+    assert decode_ids(ids, coral_vocab, lengths=lens, group_tokens=False) == [c["ungrouped"] for c in cases]
+
+
+def test_golden_edit_lm_and_beam_anchors(torch_cuda):
+    import os
+
+    from coral_b200.decoder import build_ctcdecoder
+    from coral_b200.metrics import edit_counts
+
+    rows = _golden("edit_known.json")
+    cc = edit_counts([r["hyp"] for r in rows], [r["ref"] for r in rows], "chars")
+    wc = edit_counts([r["hyp"] for r in rows], [r["ref"] for r in rows], "words")
+    for r, c, w in zip(rows, cc, wc):
+        assert c.tolist() == r["chars"] and w.tolist() == r["words"], r
+
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    data = _golden("beam_toy.json")
+    logits = np.load(os.path.join(g, "beam_toy_logits.npz"))
+    decs = {"lm": build_ctcdecoder(data["labels"], os.path.join(g, "toy.arpa")), "nolm": build_ctcdecoder(data["labels"])}
+    km = decs["lm"]._language_model.kenlm_model
+    for case in _golden("lm_toy.json"):
+        probs, _ = km.score_sentences([case["sentence"]], bos=case["bos"], eos=True)
+        assert probs[0].tolist() == [float(np.float32(x)) for x in case["log10"]]
+    for case in data["cases"]:
+        got = decs[case["decoder"]].decode_beams(logits[case["logits"]], **case["kwargs"])
+        assert [b[0] for b in got] == [b[0] for b in case["beams"]]
+        for b, ref in zip(got, case["beams"]):
+            assert abs(b[3] - ref[1]) <= 1e-4 * max(1, abs(ref[1])) and abs(b[4] - ref[2]) <= 1e-4 * max(1, abs(ref[2]))
+
+
+def test_config4_validation_properties_at_scale(torch_cuda, rng):
+    """Config 4 shape (per-sample CER filter) at 50k pairs through size-independent properties:
+    S + D + H == len(ref), I - D == len(hyp) - len(ref), identical pairs score zero, the
+    aggregate equals the sum of the per-sample counts, and a 2k subsample is bit-exact."""
+    from coral_b200 import synth
+    from coral_b200.metrics import edit_counts
+    from coral_b200.validation import validation_scores
+    from oracle import edit as oe
+
+    words = synth.make_word_list(3000)
+    n = 50_000
+    idx = rng.integers(0, len(words), size=(n, 12))
+    lens = rng.integers(3, 13, size=n)
+    refs = [" ".join(words[j] for j in idx[i, : lens[i]]) for i in range(n)]
+    hyps = [synth.corrupt_text(r, rng, 0.07) for r in refs]
+    hyps[::1000] = refs[::1000]
+    vs = validation_scores(hyps, refs, max_cer=0.6)
+    cc, wc = vs.char_counts, vs.word_counts
+    ref_len = np.array([len(r.strip()) for r in refs])
+    hyp_len = np.array([len(h.strip()) for h in hyps])
+    assert np.array_equal(cc[:, 0] + cc[:, 1] + cc[:, 3], ref_len)
+    assert np.array_equal(cc[:, 2] - cc[:, 1], hyp_len - ref_len)
+    assert (cc[::1000, :3] == 0).all() and (wc[::1000, :3] == 0).all()
+    tot = cc.sum(axis=0)
+    assert vs.cer == int(tot[0] + tot[1] + tot[2]) / int(tot[0] + tot[1] + tot[3] + tot[2])
+    assert 0.03 < vs.cer < 0.12 and vs.keep.mean() > 0.99
+    sub = rng.choice(n, size=2000, replace=False)
+    for i in sub:
+        assert tuple(cc[i]) == oe.char_counts(refs[i], hyps[i]) and tuple(wc[i]) == oe.word_counts(refs[i], hyps[i])
+    assert np.array_equal(edit_counts(hyps[:64], refs[:64], "chars"), cc[:64])
