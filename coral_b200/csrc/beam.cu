@@ -53,8 +53,18 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
 // One thread group (= one CTA of NT threads) decodes one utterance at a time and then
 // fetches the next from a global counter; `order` lets the host hand out long
 // utterances first so the tail of the batch is short.
+// minimum CTAs per SM the register allocation must allow: what shared memory permits
 template <int NT, int BW, int OUTC>
-__global__ void __launch_bounds__(NT, (768 / NT) > 0 ? (768 / NT) : 1) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
+constexpr int min_ctas() {
+  constexpr int by_smem = (int)(232448 / (sizeof(GroupShared<BW, OUTC>) + 1024));
+  constexpr int by_threads = 2048 / NT;
+  constexpr int by_regs = 65536 / (NT * 64);  // never ask for fewer than 64 registers per thread
+  constexpr int m = by_smem < by_threads ? by_smem : by_threads;
+  return m < 1 ? 1 : (m < by_regs ? m : by_regs);
+}
+
+template <int NT, int BW, int OUTC>
+__global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Dec = BeamDecoder<NT, BW, OUTC>;
   typename Dec::Sm& sm = *reinterpret_cast<typename Dec::Sm*>(smem_raw);
@@ -397,10 +407,11 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
     if (nt == 128) return launch_beam<128, 64, 192>(dec, L, B, st);
     return launch_beam<64, 64, 192>(dec, L, B, st);
   }
+  // (a <128, 104, 256> instantiation reaches 7 CTAs per SM instead of 6 for the default beam
+  // width but measured no faster -- profiles/r1_beam_kernel_tuning.md -- so it is not built)
   if (beam_width <= 128) {
     if (nt == 32) return launch_beam<32, 128, 320>(dec, L, B, st);
     if (nt == 64) return launch_beam<64, 128, 320>(dec, L, B, st);
-    if (nt == 256) return launch_beam<256, 128, 320>(dec, L, B, st);
     return launch_beam<128, 128, 320>(dec, L, B, st);
   }
   if (beam_width <= 256) {

@@ -181,7 +181,7 @@ constexpr int kNB = 64;             // score buckets over the prune window
 
 template <int BW, int OUTC>
 struct GroupShared {
-  static constexpr int HS = BW <= 32 ? 64 : (BW <= 64 ? 128 : (BW <= 128 ? 256 : (BW <= 256 ? 512 : 1024)));
+  static constexpr int HS = BW <= 32 ? 64 : (BW <= 64 ? 128 : (BW <= 128 ? 256 : (BW <= 256 ? 512 : 1024)));  // >= 2 BW
   // beams, double buffered
   double logit[2][BW];
   double lm_raw[2][BW];
@@ -468,23 +468,62 @@ struct BeamDecoder {
       }
       CORAL_GSYNC(NT);
     }
-    // argmax (first maximum) and the kept-token list in ascending id
-    CORAL_LANES(NT) {
-      for (int f = lane; f < nf; f += NT) {
-        const float* row = sm.lp[f];
-        int am = 0;
-        float best = row[0];
+    // argmax (first maximum) and the kept-token list in ascending id: eight lanes per frame
+    // scan strided elements into (best value, best index, 64-bit keep mask), then one lane per
+    // frame combines them and walks the mask's set bits.
+    {
+      float* bval = reinterpret_cast<float*>(sm.o_logit) + 3 * kChunk * 8;     // [kChunk][8]
+      uint32_t* bidx = reinterpret_cast<uint32_t*>(bval + kChunk * 8);         // [kChunk][8]
+      unsigned long long* bmask = sm.o_key;                                     // [kChunk][8]
+      CORAL_LANES(NT) {
+        for (int p = lane; p < nf * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          const float* row = sm.lp[f];
+          float best = -INFINITY;
+          uint32_t am = 0xFFFFFFFFu;
+          unsigned long long mask = 0;
 #pragma unroll 1
-        for (int v = 1; v < V; ++v) if (row[v] > best) { best = row[v]; am = v; }
-        int nk = 0;
-#pragma unroll 1
-        for (int v = 0; v < V; ++v)
-          if (row[v] >= P.token_min_logp || v == am) sm.kept[f][nk++] = (uint8_t)v;
-        sm.nkept[f] = (uint8_t)nk;
-        sm.amax[f] = (uint8_t)am;
+          for (int v = j; v < V; v += 8) {
+            const float x = row[v];
+            if (am == 0xFFFFFFFFu || x > best) { best = x; am = (uint32_t)v; }
+            if (x >= P.token_min_logp) mask |= 1ULL << v;
+          }
+          bval[p] = best;
+          bidx[p] = am;
+          bmask[p] = mask;
+        }
       }
+      CORAL_GSYNC(NT);
+      CORAL_LANES(NT) {
+        for (int f = lane; f < nf; f += NT) {
+          float best = 0.0f;
+          uint32_t am = 0xFFFFFFFFu;
+          unsigned long long mask = 0;
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t aj = bidx[f * 8 + j];
+            if (aj == 0xFFFFFFFFu) continue;
+            const float x = bval[f * 8 + j];
+            if (am == 0xFFFFFFFFu || x > best || (x == best && aj < am)) { best = x; am = aj; }
+            mask |= bmask[f * 8 + j];
+          }
+          mask |= 1ULL << am;
+          int nk = 0;
+          while (mask) {
+#if defined(__CUDA_ARCH__)
+            const int v = __ffsll((long long)mask) - 1;
+#else
+            const int v = __builtin_ctzll(mask);
+#endif
+            sm.kept[f][nk++] = (uint8_t)v;
+            mask &= mask - 1;
+          }
+          sm.nkept[f] = (uint8_t)nk;
+          sm.amax[f] = (uint8_t)am;
+        }
+      }
+      CORAL_GSYNC(NT);
     }
-    CORAL_GSYNC(NT);
   }
 
   static CORAL_DEV uint32_t rep_beam(Sm& sm, int s) { return sm.sb0[s] != kNone16 ? sm.sb0[s] : sm.sb1[s]; }
@@ -524,22 +563,36 @@ struct BeamDecoder {
   static CORAL_DEV double bucket_scale(const DecodeParams& P) {
     return d_div((double)kNB, d_add(P.beam_prune_logp < 0.0 ? -P.beam_prune_logp : 0.0, 4.0));
   }
-  static CORAL_DEV_OUTLINE void emit(Sm& sm, const OutView& o, int q, bool hist, double scale, double comb, double logit,
-                             uint32_t order, uint32_t aux, uint32_t child, uint32_t rb, uint32_t c, uint32_t kf,
-                             unsigned long long& lmax) {
+  // Candidates live in the shared-memory arrays while they fit (index < OUTC) and spill to the
+  // slot's HBM buffer past that; the slow overflow path runs only if the frame really produced
+  // more than OUTC candidates (flat logits / very wide beams).
+  static CORAL_DEV_OUTLINE void emit(Sm& sm, const OutView& g, uint32_t g_cap, int q, double scale, double comb,
+                                     double logit, uint32_t order, uint32_t aux, uint32_t child, uint32_t rb,
+                                     uint32_t c, uint32_t kf, unsigned long long& lmax) {
     const uint32_t at = atom_add(&sm.n_out[q], 1u);
     const unsigned long long k = ordered_u64(comb);
-    o.key[at] = k;
-    o.logit[at] = logit;
-    o.order[at] = order;
-    o.aux[at] = aux;
-    o.child[at] = child;
-    o.info[at] = rb | (c << 16) | (kf << 24);
-    if (hist) {  // counting-sort histogram for phase 3 (shared-memory path only)
+    const uint32_t info = rb | (c << 16) | (kf << 24);
+    if (at < (uint32_t)OUTC) {
+      sm.o_key[at] = k;
+      sm.o_logit[at] = logit;
+      sm.o_order[at] = order;
+      sm.o_aux[at] = aux;
+      sm.o_child[at] = child;
+      sm.o_info[at] = info;
+      // counting-sort histogram for phase 3
       const uint32_t b = bucket_of(sm.mhat, scale, comb);
       sm.o_pos[at] = (uint16_t)atom_add(&sm.bcnt[b], 1u);
       sm.o_bkt[at] = (uint8_t)b;
       atom_add(&sm.gcnt[b >> 3], 1u);
+    } else if (at < g_cap) {
+      g.key[at] = k;
+      g.logit[at] = logit;
+      g.order[at] = order;
+      g.aux[at] = aux;
+      g.child[at] = child;
+      g.info[at] = info;
+    } else {
+      sm.status = -4;
     }
     lmax = k > lmax ? k : lmax;
   }
@@ -547,7 +600,9 @@ struct BeamDecoder {
   // ---- phase 1: hash the live nodes of the current beam list -----------------------------
   // The hash was cleared during the previous frame's phase 3. The lane whose CAS inserts a
   // node registers it in the node list; every beam records itself in its node's slot.
-  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb, double best_lp) {
+  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb, double best_lp, const LmView* lm = nullptr,
+                                   const DecodeParams* P = nullptr, const SlotScratch* sc = nullptr, int f = 0) {
+    (void)lm; (void)P; (void)sc; (void)f;
     CORAL_LANES(NT) {
       if (lane == 0) {
         // bucket reference for this frame: last frame's best score + this frame's best
@@ -571,23 +626,12 @@ struct BeamDecoder {
     for (int i = lane; i < HS; i += NT) { sm.hkey[i] = 0; sm.sb0[i] = kNone16; sm.sb1[i] = kNone16; }
   }
 
-  // ---- phase 2: every (live node, kept token), plus repeats of nodes whose parent is dead ---
-  static CORAL_DEV void expand(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
-                               const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs,
-                               bool hist) {
-    const int K = sm.nkept[f];
-    const double bscale = bucket_scale(P);
-    const uint32_t nN = sm.nN[q];
-    CORAL_LANES(NT) {
-      if (lane == 0) {
-        // clear the other parity's per-frame counters for the next frame. This must sit behind
-        // this frame's first barrier: every thread read S[q ^ 1] (the beam count) on its way in.
-        sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
-        if (io.stats) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
-      }
-      unsigned long long lmax = 0;
-      const uint32_t n1 = nN * (uint32_t)K;
-      for (uint32_t i = lane; i < n1 + nN; i += NT) {
+  static CORAL_DEV void expand_item(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                                    const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs,
+                                    double bscale, int K, uint32_t nN, uint32_t n1, uint32_t i,
+                                    unsigned long long& lmax) {
+    {
+      {
         const bool fam2 = i >= n1;
         const uint32_t j = fam2 ? i - n1 : i / K;
         const int s = sm.ne_slot[j];
@@ -602,17 +646,17 @@ struct BeamDecoder {
           // repeat of the node's own last token (or a space on a closed word): the text does
           // not change. If the parent node is live, its (parent, c) item gathers these beams.
           const uint32_t c = tok_m == kNoTok ? (uint32_t)P.space_id : tok_m;
-          if (tok_m != kNoTok && h_find(sm, sm.ph[cur][rb]) >= 0) continue;
+          if (tok_m != kNoTok && h_find(sm, sm.ph[cur][rb]) >= 0) return;
           int k = -1;
           for (int kk = 0; kk < K; ++kk) if (sm.kept[f][kk] == c) k = kk;
-          if (k < 0) continue;
+          if (k < 0) return;
           if (b1 != kNone16) mem[nm++] = b1;  // last_char == c (None or space at the root)
           if ((int)c == P.space_id && b0 != kNone16) mem[nm++] = b0;
-          if (nm == 0) continue;
+          if (nm == 0) return;
           const uint32_t first = merge_members(sm, cur, mem, nm, (double)sm.lp[f][c], logit);
-          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
                (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax);
-          continue;
+          return;
         }
         const uint32_t k = i % K;
         const uint32_t c = sm.kept[f][k];
@@ -621,11 +665,11 @@ struct BeamDecoder {
           if (b0 != kNone16) mem[nm++] = b0;
           if (b1 != kNone16) mem[nm++] = b1;
           const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
-          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
+          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
                k * nb + first, 0u, 0u, rb, c, 0u, lmax);
-          continue;
+          return;
         }
-        if ((int)c == P.space_id && wlen_m == 0) continue;  // a space after a closed word never extends
+        if ((int)c == P.space_id && wlen_m == 0) return;  // a space after a closed word never extends
         if (b0 != kNone16) mem[nm++] = b0;
         if (b1 != kNone16 && tok_m != c) mem[nm++] = b1;
         const int cs = h_find(sm, child_hash(sm.nh[cur][rb], c));
@@ -633,12 +677,12 @@ struct BeamDecoder {
           if (sm.sb1[cs] != kNone16) mem[nm++] = sm.sb1[cs];
           if ((int)c == P.space_id && sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
         }
-        if (nm == 0) continue;
+        if (nm == 0) return;
         const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
         const uint32_t order = k * nb + first;
         if (cs >= 0) {
           const uint32_t crb = rep_beam(sm, cs);
-          emit(sm, outs, q, hist, bscale,
+          emit(sm, outs, sc.outs_cap, q, bscale,
                d_add(logit, d_add(sm.lm_raw[cur][crb],
                                   partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])))),
                logit, order, 0u, crb, rb, c, 1u, lmax);
@@ -661,7 +705,7 @@ struct BeamDecoder {
             raw_new = nr.lm_raw;
             sc.bnd[bnd_new] = nr;
           }
-          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, 0u, rb, c, 3u, lmax);
+          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, 0u, rb, c, 3u, lmax);
         } else {
           // a letter extends the partial word: roll the word hash, probe the lexicon
           uint32_t nfl = 0, nwid = 0;
@@ -686,9 +730,30 @@ struct BeamDecoder {
             }
             ps = partial_score(P, wlen_m + P.label_ncp[c], nfl);
           }
-          emit(sm, outs, q, hist, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
+          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
                2u | (nfl << 2), lmax);
         }
+      }
+    }
+  }
+
+  // ---- phase 2: every (live node, kept token), plus repeats of nodes whose parent is dead ---
+  static CORAL_DEV void expand(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                               const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs) {
+    const int K = sm.nkept[f];
+    const double bscale = bucket_scale(P);
+    const uint32_t nN = sm.nN[q];
+    CORAL_LANES(NT) {
+      if (lane == 0) {
+        // clear the other parity's per-frame counters for the next frame. This must sit behind
+        // this frame's first barrier: every thread read S[q ^ 1] (the beam count) on its way in.
+        sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
+        if (io.stats) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
+      }
+      unsigned long long lmax = 0;
+      const uint32_t n1 = nN * (uint32_t)K;
+      for (uint32_t i = lane; i < n1 + nN; i += NT) {
+        expand_item(sm, lm, P, sc, io, f, cur, q, nb, outs, bscale, K, nN, n1, i, lmax);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
@@ -701,7 +766,14 @@ struct BeamDecoder {
   static CORAL_DEV_OUTLINE void select_overflow(Sm& sm, const DecodeParams& P, const OutView& g, int q,
                                         unsigned long long thr) {
     const uint32_t n = sm.n_out[q];
-    uint32_t* hist = reinterpret_cast<uint32_t*>(sm.o_key);  // 256 bins; o_key is unused until the pull
+    CORAL_LANES(NT) {
+      for (uint32_t i = lane; i < (uint32_t)OUTC; i += NT) {
+        g.key[i] = sm.o_key[i]; g.logit[i] = sm.o_logit[i]; g.order[i] = sm.o_order[i];
+        g.aux[i] = sm.o_aux[i]; g.child[i] = sm.o_child[i]; g.info[i] = sm.o_info[i];
+      }
+    }
+    CORAL_GSYNC(NT);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sm.o_key);  // 256 bins; o_key is free until the pull
     CORAL_LANES(NT) { if (lane == 0) { sm.sel_prefix = 0; sm.sel_mask = 0; sm.sel_need = (uint32_t)P.beam_width; sm.sel_n = 0; } }
     CORAL_GSYNC(NT);
     for (int pass = 0; pass < 8; ++pass) {
@@ -914,21 +986,14 @@ struct BeamDecoder {
                                    const UttIO& io, int f, int cur, int q, uint32_t nb) {
     PhaseTimer pt;
     pt.start(io.stats);
-    hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]]);
+    hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]], &lm, &P, &sc, f);
     pt.mark(8);
-    const uint32_t n_slots = sm.nN[q] * ((uint32_t)sm.nkept[f] + 1u);
-    const bool in_smem = n_slots <= (uint32_t)OUTC;
-    if (!in_smem && n_slots > sc.outs_cap) {
-      CORAL_LANES(NT) { if (lane == 0) sm.status = -4; }
-      CORAL_GSYNC(NT);
-      return;
-    }
-    const OutView outs = in_smem ? smem_outs(sm) : sc.outs_g;
-    expand(sm, lm, P, sc, io, f, cur, q, nb, outs, in_smem);
+    expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
     pt.mark(9);
+    if (sm.status != 0) return;  // uniform: written before the barrier that ends expand
     const unsigned long long thr = prune_key(sm, P, q);
-    if (!in_smem) {
-      select_overflow(sm, P, outs, q, thr);
+    if (sm.n_out[q] > (uint32_t)OUTC) {
+      select_overflow(sm, P, sc.outs_g, q, thr);
       rebucket(sm, P, q);
       pt.mark(10);
     }
@@ -940,7 +1005,7 @@ struct BeamDecoder {
                                      const UttIO& io, int cur, int q, uint32_t nb) {
     hash_beams(sm, cur, q, nb, 0.0);
     const uint32_t nN = sm.nN[q];
-    const OutView outs = smem_outs(sm);  // nN <= beam_width <= OUTC
+    const OutView outs = sc.outs_g;  // never reached: at most beam_width <= OUTC candidates here
     const double bscale = bucket_scale(P);
     CORAL_LANES(NT) {
       unsigned long long lmax = 0;
@@ -978,7 +1043,7 @@ struct BeamDecoder {
           comb = d_add(logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
         }
         // text node: the open-word node itself, or the parent of a closed-word node
-        emit(sm, outs, q, true, bscale, comb, logit, first, 0u,
+        emit(sm, outs, sc.outs_cap, q, bscale, comb, logit, first, 0u,
              open_or_root ? sm.node[cur][rb] : sc.node_parent[sm.node[cur][rb]], rb, 0u, 0u, lmax);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);

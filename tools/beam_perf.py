@@ -40,7 +40,7 @@ if os.environ.get("CORAL_PHASES"):
     names = ["hash", "expand", "ovf-select", "bucket", "scatter", "rank+commit", "grow", "stage"]
     tot = st[8:16].sum()
     print("per-frame cycles (thread 0): " + ", ".join(f"{n}={st[8+i]/fr:.0f}" for i, n in enumerate(names)) + f"  total={tot/fr:.0f}")
-    ops = ["trie_find", "lm_word_score", "trie_add(expand)", "lex_find", "trie_add(commit)"]
+    ops = ["-", "lm_word_score", "-", "lex_find", "-"]
     print("op latency (cycles/call, calls/frame): " + ", ".join(
         f"{n}={st[16+i]/max(st[24+i],1):.0f}x{st[24+i]/fr:.2f}" for i, n in enumerate(ops)))
     print(f"per frame: ext={st[0]/fr:.1f} lm_scorings={st[1]/fr:.2f} ngram_probes={st[2]/fr:.2f} lex_probes={st[4]/fr:.2f} nodes={st[5]/fr:.2f} growths/utt={st[7]/a.utts:.2f}")
