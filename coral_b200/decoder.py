@@ -37,7 +37,8 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 MAX_BEAM_WIDTH = 512
-H2D_CHUNK = 1024  # utterances per host->device chunk when the logits arrive from the host
+H2D_CHUNK = 4096  # utterances per host->device chunk when the logits arrive from the host
+# (large chunks: a launch with few utterances per CTA is dominated by its longest utterances)
 
 
 def _torch():
@@ -190,7 +191,7 @@ class BeamSearchDecoderCTC:
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         d_stats = torch.zeros(32, dtype=torch.int64, device=dev) if collect_stats else None
         B = logits.shape[0]
-        if logits.device.type == "cpu" and B > 2 * H2D_CHUNK and logits.dtype == torch.float32:
+        if logits.device.type == "cpu" and B >= 2 * H2D_CHUNK and logits.dtype == torch.float32:
             # host logits: stream them in chunks on a copy stream so that the H2D transfer of
             # chunk k+1 overlaps the decode of chunk k (pinned memory makes the copies async)
             main = torch.cuda.current_stream(dev)
@@ -251,6 +252,26 @@ class BeamSearchDecoderCTC:
         if events is not None:
             events[1].record()
         return d_n, d_logit, d_comb, d_tok, d_lens, d_status
+
+    def device_tokens_to_text(self, d_tok, d_lens) -> list[str]:
+        """Winning token rows still on the device ``[B, T]`` uint8 + lengths ``[B]`` -> strings:
+        the alphabet lookup and the compaction run on the GPU, one flat code-point buffer comes
+        back, and the host only decodes UTF-32 and slices."""
+        torch = _torch()
+        if not self._single_cp:
+            return self.tokens_to_text(d_tok.cpu().numpy(), d_lens.cpu().numpy())
+        B, T = d_tok.shape
+        dev = d_tok.device
+        if getattr(self, "_d_cp_table", None) is None or self._d_cp_table.device != dev:
+            self._d_cp_table = torch.from_numpy(self._cp_table.astype(np.int64)).to(dev).to(torch.int32)
+        lens = d_lens.to(torch.int64)
+        mask = torch.arange(T, device=dev)[None, :] < lens[:, None]
+        flat = self._d_cp_table[d_tok[mask].to(torch.int64)]
+        off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=off[1:])
+        text = flat.cpu().numpy().view(np.uint32).tobytes().decode("utf-32-le")
+        o = off.cpu().tolist()
+        return [text[a:b] for a, b in zip(o[:-1], o[1:])]
 
     def tokens_to_text(self, tokens: np.ndarray, lens: np.ndarray) -> list[str]:
         """Alphabet indices -> strings for ``[N, T]`` token rows with ``[N]`` lengths."""
@@ -343,15 +364,19 @@ class BeamSearchDecoderCTC:
         arrays, or (extension) a padded ``[B, T_max, V]`` array/tensor with ``lengths``."""
         if hotwords:
             raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
-        if lengths is not None:
-            out = self.decode_padded(logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1)
-        else:
+        if lengths is None:
             logits_list = [np.asarray(lg) for lg in logits_list]
             if not logits_list:
                 return []
-            buf, lens = self._pad(logits_list)
-            out = self.decode_padded(buf, lens, beam_width, beam_prune_logp, token_min_logp, n_best=1)
-        return self.tokens_to_text(out.tokens[:, 0, :], out.lens[:, 0])
+            logits_list, lengths = self._pad(logits_list)
+        d_n, d_logit, d_comb, d_tok, d_lens, d_status, _ = self.decode_padded(
+            logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1, to_host=False)
+        texts = self.device_tokens_to_text(d_tok[:, 0, :], d_lens[:, 0])
+        status = d_status.cpu().numpy()
+        if status.any():
+            bad = np.nonzero(status)[0]
+            raise _lib.CoralError(int(status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
+        return texts
 
     # ------------------------------------------------------------- serialisation
     def save_to_dir(self, filepath: str) -> None:

@@ -61,7 +61,10 @@ def edit_counts_spans_device(ref_cps, ref_beg, ref_end, hyp_cps, hyp_beg, hyp_en
     return sdih[:n_pairs], status[:n_pairs]
 
 
-_UPLOAD_CACHE: list = []  # the reference calls cer() then wer() on the same lists: marshal once
+# The reference calls cer() and then wer() on the same two lists (R:src/coral/validation.py:137-140,
+# R:src/coral/evaluate.py:195-198): the code points marshalled for cer() are reused by the wer()
+# that follows. cer() starts a fresh cache, so nothing survives from one evaluation to the next.
+_UPLOAD_CACHE: list = []
 
 
 def _upload(strings, dev):
@@ -122,6 +125,7 @@ def _rate_from_counts(sdih: np.ndarray, normalise: bool) -> float:
 
 def cer(predictions: c.Iterable[str], labels: c.Iterable[str], normalise: bool = True) -> float:
     """Character error rate, aggregated (R:src/coral/metrics.py:8-33)."""
+    _UPLOAD_CACHE.clear()
     return _rate_from_counts(edit_counts(predictions, labels, "chars"), normalise)
 
 

@@ -30,8 +30,11 @@ class ValidationScores:
 
 
 def validation_scores(predictions, labels, max_cer: float = 0.6, normalise: bool = True) -> ValidationScores:
+    from . import metrics as _m
+
     predictions = list(predictions)
     labels = list(labels)
+    _m._UPLOAD_CACHE.clear()
     cc = edit_counts(predictions, labels, "chars")
     wc = edit_counts(predictions, labels, "words")
     asr_cer = per_sample_rates(cc, normalise)
