@@ -125,7 +125,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -133,9 +133,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_from=0.0, t_to=float("inf")):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -143,7 +143,9 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t_from <= ts <= t_to):
+                continue
             p = [x.strip() for x in r.split(",")]
             if len(p) < 9:
                 continue
@@ -328,12 +330,13 @@ def run_ours(args, rank, world, local_rank):
             raise SystemExit(f"PARITY FAILURE against the oracle on the CPU sample: {parity}")
 
     # ---- timed: device-resident
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~100 ms to come up
     for _ in range(max(args.warmup, 3)):
         totals, d_status = step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_clock0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -341,7 +344,6 @@ def run_ours(args, rank, world, local_rank):
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     beam_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
     assert int(d_status.sum().item()) == 0
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -359,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
         hyps, cer_v, wer_v = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    # clocks sampled during the two timed regions (device-resident steps and end-to-end steps)
+    clocks = sampler.stop(t_clock0, time.time()) if rank == 0 else None
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
