@@ -282,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
         """Inputs resident in HBM; everything stays on the device."""
         if time_kernel:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # decode_padded: argsort of lengths (torch) + classify kernel + beam-search kernel
+        # decode_padded: argsort of lengths (torch) + the beam-search kernel
         d_order = torch.argsort(d_len, descending=True).to(torch.int32)
         outs = dec.decode_launch(d_logits, d_len, d_order, beam_width=args.beam, n_best=1,
                                  events=(e0, e1) if time_kernel else None)
@@ -412,9 +412,9 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int(h_logits.numel() * 4 + B * 4 + 2 * (r_cps.nbytes + r_off.nbytes) + 2 * (hyp_chars * 4 + 8 * (B + 1))),
                     "d2h_bytes_per_step": int(B * Tm + B * (4 + 8 + 8 + 4 + 4) + 2 * B * 20),
                     "audio_s_per_s": world * audio * e2e_steps / e2e_s, "steps": e2e_steps},
-            "gpu_launches": 4 * args.steps,
-            "kernels_per_step": ["classify_input_kernel", "beam_search_kernel", "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
-            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<128,128,320> (+ classify_input_kernel, same event pair)",
+            "gpu_launches": 3 * args.steps,
+            "kernels_per_step": ["beam_search_kernel", "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
+            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<128,128,320>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes,

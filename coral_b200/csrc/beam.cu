@@ -19,7 +19,8 @@ struct BeamLaunch {
   const float* logits;
   const int32_t* lengths;
   const int32_t* order;
-  const int32_t* is_prob;
+  const int32_t* ready;     // streamed input: number of utterances whose logits have landed (or NULL)
+  int32_t ready_chunk;      // utterances per host->device chunk
   int32_t B;
   int32_t* out_n;
   double* out_logit;
@@ -41,9 +42,8 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
   size_t o = 0;
   off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
   off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
-  off[2] = o;                                              // (unused)
+  off[2] = o; o = align16(o + (size_t)ch_size * 4);        // row sums of the utterance being classified [T_max]
   off[3] = o;                                              // (unused)
-  (void)ch_size;
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
   off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
   off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kern
     uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
     sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
     sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
+    sc.rowsum = reinterpret_cast<float*>(base + off[2]);
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
     sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
     sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
@@ -93,10 +94,31 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kern
     const int i = sm.utt;
     if (i >= L.B) break;
     const int u = L.order ? L.order[i] : i;
+    if (L.ready != nullptr) {
+      // streamed input: wait until the copy stream has delivered this utterance's chunk
+      // (bounded: a copier that never delivers must not hang the device -- about 20 s)
+      if (threadIdx.x == 0) {
+        const int need = min(L.B, (u / L.ready_chunk + 1) * L.ready_chunk);
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*reinterpret_cast<const volatile int32_t*>(L.ready) < need) {
+          __nanosleep(500);
+          if (clock64() - t0 > (40LL << 30)) { ok = 0; break; }
+        }
+        __threadfence();
+        sm.status = ok;
+      }
+      group_sync<NT>();
+      const int arrived = sm.status;
+      group_sync<NT>();
+      if (!arrived) {
+        if (threadIdx.x == 0) { L.out_n[u] = 0; L.out_status[u] = CORAL_ECUDA; }
+        continue;
+      }
+    }
     UttIO io;
     io.logits = L.logits + (size_t)u * L.P.T_max * L.P.V;
     io.T = L.lengths[u];
-    io.is_prob = L.is_prob ? L.is_prob[u] : 0;
     io.out_n = L.out_n + u;
     io.out_logit = L.out_logit + (size_t)u * L.P.n_best;
     io.out_comb = L.out_comb + (size_t)u * L.P.n_best;
@@ -106,55 +128,6 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kern
     io.stats = L.stats;
     Dec::decode(sm, L.lm, L.P, sc, io);
     group_sync<NT>();
-  }
-}
-
-// ---- pyctcdecode's input check: math.isclose(logits.sum(axis=1).mean(), 1) -------------
-// (SURVEY A5 step 2). Both reductions are float32 in numpy's pairwise order so that the
-// float32 mean -- which passes the test only when it is exactly 1.0f -- is reproduced.
-__device__ float pw_leaf(const float* a, int n) {
-  if (n < 8) {
-    float r = 0.0f;
-    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
-    return r;
-  }
-  float r[8];
-  for (int j = 0; j < 8; ++j) r[j] = a[j];
-  int i = 8;
-  for (; i < n - (n % 8); i += 8)
-    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
-  float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                      __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-  for (; i < n; ++i) s = __fadd_rn(s, a[i]);
-  return s;
-}
-__device__ float pw_sum(const float* a, int n) {
-  if (n <= 128) return pw_leaf(a, n);
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return __fadd_rn(pw_sum(a, n2), pw_sum(a + n2, n - n2));
-}
-
-__global__ void classify_input_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lengths,
-                                      int B, int T_max, int V, float* __restrict__ rowsum,
-                                      int32_t* __restrict__ is_prob) {
-  const int u = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32);
-  const int lane = threadIdx.x % 32;
-  if (u >= B) return;
-  const int T = lengths[u];
-  float* rs = rowsum + (size_t)u * T_max;
-  for (int t = lane; t < T; t += 32) {
-    const float* row = logits + ((size_t)u * T_max + t) * V;
-    rs[t] = V <= 128 ? pw_leaf(row, V) : pw_sum(row, V);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    int p = 0;
-    if (T > 0) {
-      const float mean = __fdiv_rn(pw_sum(rs, T), (float)T);
-      p = mean == 1.0f ? 1 : 0;
-    }
-    is_prob[u] = p;
   }
 }
 
@@ -175,7 +148,7 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   const uint64_t bw = (uint64_t)L.P.beam_width;
   uint32_t node_cap = (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu);
   uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
-  uint32_t ch_size = 0;
+  uint32_t ch_size = 9 * (uint32_t)T + 16;  // floats of row-sum scratch: [T] sums + [T][8] partials
   uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
   size_t off[7];
   const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
@@ -300,8 +273,6 @@ int32_t coral_decoder_free(coral_decoder* d) {
   if (d->d_lex) cudaFree(d->d_lex);
   if (d->d_scratch) cudaFree(d->d_scratch);
   if (d->d_work) cudaFree(d->d_work);
-  if (d->d_rowsum) cudaFree(d->d_rowsum);
-  if (d->d_is_prob) cudaFree(d->d_is_prob);
   delete d;
   return CORAL_OK;
 }
@@ -328,8 +299,10 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
                               double beam_prune_logp, double token_min_logp, int32_t prune_history,
                               int32_t input_mode, int32_t n_best, int32_t* out_n_beams_dev,
                               double* out_logit_score_dev, double* out_lm_score_dev, uint8_t* out_tokens_dev,
-                              int32_t* out_lens_dev, int32_t* out_status_dev, uint64_t* stats_dev, void* stream) {
+                              int32_t* out_lens_dev, int32_t* out_status_dev, uint64_t* stats_dev,
+                              const int32_t* ready_dev, int32_t ready_chunk, void* stream) {
   if (!dec) return fail(CORAL_EARG, "coral_ctc_beam_decode: null decoder");
+  if (ready_dev && ready_chunk < 1) return fail(CORAL_EARG, "ready_chunk must be >= 1 with a ready counter");
   if (B < 0 || T_max < 0) return fail(CORAL_EARG, "negative batch or frame count");
   if (V != dec->P.V)
     return fail(CORAL_EARG, "Input logits have vocabulary size " + std::to_string(V) + ", but the alphabet is size " +
@@ -370,30 +343,8 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.out_len = out_lens_dev;
   L.out_status = out_status_dev;
   L.stats = reinterpret_cast<unsigned long long*>(stats_dev);
-
-  if (input_mode == 0) {
-    const size_t need = (size_t)B * L.P.T_max;
-    if (dec->rowsum_elems < need) {
-      CORAL_CUDA_OK(cudaDeviceSynchronize());
-      if (dec->d_rowsum) cudaFree(dec->d_rowsum);
-      dec->d_rowsum = nullptr;
-      CORAL_CUDA_OK(cudaMalloc(&dec->d_rowsum, need * sizeof(float)));
-      dec->rowsum_elems = need;
-    }
-    if (dec->is_prob_elems < (size_t)B) {
-      CORAL_CUDA_OK(cudaDeviceSynchronize());
-      if (dec->d_is_prob) cudaFree(dec->d_is_prob);
-      dec->d_is_prob = nullptr;
-      CORAL_CUDA_OK(cudaMalloc(&dec->d_is_prob, (size_t)B * sizeof(int32_t)));
-      dec->is_prob_elems = (size_t)B;
-    }
-    const int threads = 128;
-    const unsigned blocks = (unsigned)(((size_t)B * 32 + threads - 1) / threads);
-    classify_input_kernel<<<blocks, threads, 0, st>>>(logits_dev, lengths_dev, B, L.P.T_max, V, dec->d_rowsum,
-                                                      dec->d_is_prob);
-    CORAL_CUDA_OK(cudaGetLastError());
-    L.is_prob = dec->d_is_prob;
-  }
+  L.ready = ready_dev;
+  L.ready_chunk = ready_chunk > 0 ? ready_chunk : 1;
 
   // threads per utterance: CORAL_BEAM_NT overrides the default (tuning knob)
   int nt = 0;

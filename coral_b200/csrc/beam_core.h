@@ -126,7 +126,7 @@ struct DecodeParams {
   int32_t beam_width;
   int32_t n_best;       // beams written per utterance (<= beam_width)
   int32_t T_max;        // row pitch of logits [B, T_max, V] and of out_tokens
-  int32_t input_mode;   // 0 auto (is_prob[] decides), 1 logits, 2 probabilities
+  int32_t input_mode;   // 0 auto (pyctcdecode's test, evaluated per utterance), 1 logits, 2 probabilities
   int32_t score_boundary;
   float token_min_logp;  // compared in float32
   double beam_prune_logp;
@@ -157,13 +157,13 @@ struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after 
   uint32_t* node_info;  // tok | bnd << 8
   BndRec* bnd;
   OutView outs_g;       // overflow for frames with more candidates than fit in smem
+  float* rowsum;        // [T_max] row sums of the utterance being classified
   uint32_t node_cap, bnd_cap, outs_cap;
 };
 
 struct UttIO {
   const float* logits;  // [T, V] of this utterance
   int32_t T;
-  int32_t is_prob;
   // outputs
   int32_t* out_n;       // scalar: number of final beams
   double* out_logit;    // [n_best]
@@ -224,7 +224,7 @@ struct GroupShared {
   uint32_t node_count, bnd_count;
   uint32_t sel_need, sel_eq, sel_cut, sel_n;
   uint32_t gsum[16];
-  int32_t status, utt;
+  int32_t status, utt, is_prob;
   uint32_t cnt[8];  // work counters of this utterance (flushed to UttIO::stats at its end)
   unsigned long long opc[8];  // tuning: cycles spent inside selected device operations
   uint32_t opn[8];            //         and how many times each ran
@@ -283,6 +283,58 @@ static CORAL_DEV_OUTLINE double lm_word_score(const LmView& lm, const DecodePara
   }
   if (cnt) { atom_add(&cnt[1], 1u); atom_add(&cnt[2], (uint32_t)np); }
   return d_add(d_mul(d_mul(P.alpha, x), P.log_base_change), P.beta);
+}
+
+// numpy's float32 pairwise summation (np.add.reduce over a contiguous axis): n < 8 sequential;
+// n <= 128 eight strided accumulators combined as a balanced tree, remainder in order; larger n
+// split in halves (the left half rounded down to a multiple of 8), recursively.
+CORAL_HD float np_pairwise_leaf(const float* a, int n) {
+  if (n < 8) {
+    float r = 0.0f;
+    for (int i = 0; i < n; ++i) r = f32_add(r, a[i]);
+    return r;
+  }
+  float r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = f32_add(r[j], a[i + j]);
+  float s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])), f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
+  for (; i < n; ++i) s = f32_add(s, a[i]);
+  return s;
+}
+CORAL_HD float np_pairwise_sum(const float* a, int n) {
+  // iterative form of the recursion (explicit stack of pending right halves)
+  // post-order evaluation: leaves return values that are added in the recursion's order
+  struct Frame { const float* a; int n; int state; float left; };
+  Frame fr[32];
+  int sp = 0;
+  fr[0] = Frame{a, n, 0, 0.0f};
+  float ret = 0.0f;
+  while (sp >= 0) {
+    Frame& f = fr[sp];
+    if (f.n <= 128) {
+      ret = np_pairwise_leaf(f.a, f.n);
+      --sp;
+      continue;
+    }
+    int n2 = f.n / 2;
+    n2 -= n2 % 8;
+    if (f.state == 0) {
+      f.state = 1;
+      fr[sp + 1] = Frame{f.a, n2, 0, 0.0f};
+      ++sp;
+    } else if (f.state == 1) {
+      f.left = ret;
+      f.state = 2;
+      fr[sp + 1] = Frame{f.a + n2, f.n - n2, 0, 0.0f};
+      ++sp;
+    } else {
+      ret = f32_add(f.left, ret);
+      --sp;
+    }
+  }
+  return ret;
 }
 
 // Op timing for tuning: average latency of selected operations (trie find / insert, LM word
@@ -385,7 +437,7 @@ struct BeamDecoder {
     }
     CORAL_GSYNC(NT);
     const float lo = -34.538776f;  // float32(log(1e-15))
-    const bool as_prob = P.input_mode == 2 || (P.input_mode == 0 && io.is_prob);
+    const bool as_prob = P.input_mode == 2 || (P.input_mode == 0 && sm.is_prob);
     if (as_prob) {
       CORAL_LANES(NT) {
         for (int i = lane; i < nf * V; i += NT) {
@@ -1081,6 +1133,75 @@ struct BeamDecoder {
     return nf;
   }
 
+  // ---- pyctcdecode's probabilities-vs-logits test for one utterance -> sm.is_prob.
+  // Row sums replay numpy's float32 order (eight strided accumulators = eight lanes per row,
+  // coalesced reads; balanced combine; remainder in order). The mean of the row sums is first
+  // bounded with a double-precision total: unless it lies within 1e-3 of 1 the float32 mean
+  // cannot be exactly 1.0f whatever the summation order (float32 pairwise error is < 1e-5
+  // relative), and only then one lane replays numpy's pairwise order over the T row sums.
+  static CORAL_DEV_OUTLINE void classify_input(Sm& sm, const DecodeParams& P, const SlotScratch& sc, const UttIO& io) {
+    static_assert(OUTC >= NT, "the candidate arrays double as per-lane scratch");
+    const int V = P.V, T = io.T;
+    float* part = sc.rowsum + T;  // [T][8] strided partial sums
+    const int main_n = V - (V % 8);
+    if (V >= 8 && V <= 128) {
+      CORAL_LANES(NT) {
+        for (int p = lane; p < T * 8; p += NT) {
+          const int f = p >> 3, j = p & 7;
+          const float* row = io.logits + (size_t)f * V;
+          float r = row[j];
+#pragma unroll 4
+          for (int i = j + 8; i < main_n; i += 8) r = f32_add(r, row[i]);
+          part[p] = r;
+        }
+      }
+      CORAL_GSYNC(NT);
+    }
+    double* dsum = reinterpret_cast<double*>(sm.o_logit);  // [NT], candidate arrays are idle here
+    double* dabs = reinterpret_cast<double*>(sm.o_key);    // [NT]
+    CORAL_LANES(NT) {
+      double ds = 0.0, da = 0.0;
+      for (int f = lane; f < T; f += NT) {
+        const float* row = io.logits + (size_t)f * V;
+        float s;
+        if (V >= 8 && V <= 128) {
+          const float* r = part + f * 8;
+          s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])), f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
+          for (int i = main_n; i < V; ++i) s = f32_add(s, row[i]);
+        } else {
+          s = np_pairwise_sum(row, V);
+        }
+        sc.rowsum[f] = s;
+        ds += (double)s;
+        da += (double)(s < 0.0f ? -s : s);
+      }
+      dsum[lane] = ds;
+      dabs[lane] = da;
+    }
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) {
+      if (lane == 0) {
+        int p = 0;
+        if (T > 0) {
+          double ds = 0.0, da = 0.0;
+          for (int k = 0; k < NT; ++k) { ds += dsum[k]; da += dabs[k]; }
+          const double dev = ds / T - 1.0;
+          if ((dev < 0 ? -dev : dev) <= 1e-3 * (1.0 + da / T)) {  // false for NaN: not probabilities
+            const float tot = np_pairwise_sum(sc.rowsum, T);
+#if defined(__CUDA_ARCH__)
+            const float mean = __fdiv_rn(tot, (float)T);
+#else
+            const float mean = tot / (float)T;
+#endif
+            p = mean == 1.0f ? 1 : 0;
+          }
+        }
+        sm.is_prob = p;
+      }
+    }
+    CORAL_GSYNC(NT);
+  }
+
   // ---- whole utterance ---------------------------------------------------------------------------
   static CORAL_DEV void decode(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc, const UttIO& io) {
     CORAL_LANES(NT) {
@@ -1116,6 +1237,10 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
+    // pyctcdecode's input test: math.isclose(logits.sum(axis=1).mean(), 1),
+    // which a float32 mean passes only when it is exactly 1.0f -- so both reductions replay
+    // numpy's summation order. Done per utterance here (no batch-wide pre-pass).
+    if (P.input_mode == 0) classify_input(sm, P, sc, io);
     int cur = 0, q = 0;
     uint32_t nb = 1;
     bool failed = false;

@@ -28,8 +28,5 @@ struct coral_decoder {
   uint32_t n_slots = 0;
   uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0;
   int32_t* d_work = nullptr;
-  float* d_rowsum = nullptr;   // [B * T_max] for the probabilities-vs-logits detection
-  int32_t* d_is_prob = nullptr;
-  size_t rowsum_elems = 0, is_prob_elems = 0;
   uint64_t device_bytes = 0;
 };

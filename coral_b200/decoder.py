@@ -37,7 +37,7 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 MAX_BEAM_WIDTH = 512
-H2D_CHUNK = 4096  # utterances per host->device chunk when the logits arrive from the host
+H2D_CHUNK = 512  # utterances per host->device chunk when the logits arrive from pinned host memory
 # (large chunks: a launch with few utterances per CTA is dominated by its longest utterances)
 
 
@@ -191,26 +191,35 @@ class BeamSearchDecoderCTC:
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         d_stats = torch.zeros(32, dtype=torch.int64, device=dev) if collect_stats else None
         B = logits.shape[0]
-        if logits.device.type == "cpu" and B >= 2 * H2D_CHUNK and logits.dtype == torch.float32:
-            # host logits: stream them in chunks on a copy stream so that the H2D transfer of
-            # chunk k+1 overlaps the decode of chunk k (pinned memory makes the copies async)
+        if (logits.device.type == "cpu" and B >= 2 * H2D_CHUNK and logits.dtype == torch.float32
+                and logits.is_contiguous() and logits.is_pinned()):
+            # Pinned host logits: ONE launch over the whole batch, fed by a copy stream. The
+            # copier delivers H2D_CHUNK utterances at a time and bumps a device counter after
+            # each chunk; thread groups wait for their utterance's chunk (include/coral_b200.h,
+            # ``ready_dev``), so the decode of chunk k overlaps the transfer of chunk k+1.
             main = torch.cuda.current_stream(dev)
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
-            parts = []
-            for a0 in range(0, B, H2D_CHUNK):
-                b0 = min(B, a0 + H2D_CHUNK)
-                with torch.cuda.stream(self._copy_stream):
-                    d_chunk = logits[a0:b0].to(device=dev, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self._copy_stream)
-                d_chunk.record_stream(main)
-                main.wait_event(ev)
-                cl = d_len[a0:b0]
-                order = torch.argsort(cl, descending=True).to(torch.int32)
-                parts.append(self.decode_launch(d_chunk, cl, order, beam_width, beam_prune_logp, token_min_logp,
-                                                n_best, input_mode, d_stats))
-            d_n, d_logit, d_comb, d_tok, d_lens, d_status = (torch.cat([p[k] for p in parts]) for k in range(6))
+            copy = self._copy_stream
+            n_chunks = (B + H2D_CHUNK - 1) // H2D_CHUNK
+            d_logits = torch.empty(logits.shape, dtype=torch.float32, device=dev)
+            d_ready = torch.zeros(1, dtype=torch.int32, device=dev)
+            marks = torch.tensor([min(B, (k + 1) * H2D_CHUNK) for k in range(n_chunks)], dtype=torch.int32).pin_memory()
+            copy.wait_stream(main)  # buffers allocated / zeroed on the main stream
+            with torch.cuda.stream(copy):
+                for k in range(n_chunks):
+                    a0, b0 = k * H2D_CHUNK, min(B, (k + 1) * H2D_CHUNK)
+                    d_logits[a0:b0].copy_(logits[a0:b0], non_blocking=True)
+                    d_ready.copy_(marks[k:k + 1], non_blocking=True)
+            d_logits.record_stream(copy)
+            d_ready.record_stream(copy)
+            # chunk-major work order, longest first inside a chunk
+            chunk_id = torch.arange(B, device=dev, dtype=torch.int64) // H2D_CHUNK
+            d_order = torch.argsort(chunk_id * (int(logits.shape[1]) + 1) - d_len.to(torch.int64)).to(torch.int32)
+            self._keepalive = (logits, marks)  # host buffers stay alive until the copies ran
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
+                d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats,
+                ready=(d_ready, H2D_CHUNK))
         else:
             d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
             d_order = torch.argsort(d_len, descending=True).to(torch.int32)
@@ -228,9 +237,10 @@ class BeamSearchDecoderCTC:
 
     def decode_launch(self, d_logits, d_len, d_order, beam_width: int = DEFAULT_BEAM_WIDTH,
                       beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
-                      n_best: int = 1, input_mode: int = 0, d_stats=None, events=None):
+                      n_best: int = 1, input_mode: int = 0, d_stats=None, events=None, ready=None):
         """Queue one batched decode on device-resident inputs (asynchronous). ``events`` =
-        (start, end) ``torch.cuda.Event`` recorded around the library call on the launching stream."""
+        (start, end) ``torch.cuda.Event`` recorded around the library call on the launching stream.
+        ``ready`` = (int32 device counter, chunk) for logits still arriving on another stream."""
         torch = _torch()
         h = self._handle()
         dev = d_logits.device
@@ -248,7 +258,9 @@ class BeamSearchDecoderCTC:
             h, d_logits.data_ptr(), d_len.data_ptr(), d_order.data_ptr() if d_order is not None else None, B,
             int(T_max), V, int(beam_width), float(beam_prune_logp), float(token_min_logp), 0, int(input_mode),
             int(n_best), d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
-            d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None, _lib.stream_ptr(dev)))
+            d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None,
+            ready[0].data_ptr() if ready is not None else None, int(ready[1]) if ready is not None else 0,
+            _lib.stream_ptr(dev)))
         if events is not None:
             events[1].record()
         return d_n, d_logit, d_comb, d_tok, d_lens, d_status

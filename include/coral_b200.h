@@ -87,7 +87,8 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *   logits_dev   float32 [B, T_max, V]; rows >= lengths[b] are ignored
  *   lengths_dev  int32 [B]
  *   order_dev    int32 [B] processing order (longest first balances the tail) or NULL
- *   input_mode   0 = pyctcdecode's auto-detection of probabilities vs logits, 1 logits, 2 probs
+ *   input_mode   0 = pyctcdecode's auto-detection of probabilities vs logits (per utterance,
+ *                inside the kernel), 1 logits, 2 probs
  *   n_best       beams returned per utterance (<= beam_width)
  * Outputs (device, caller-allocated):
  *   out_n_beams     int32 [B]           number of final beams (<= beam_width)
@@ -100,6 +101,13 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *                   frames, lexicon probes, trie nodes, LM boundary records, child-table
  *                   growths (work counters of SURVEY 8d); [8..15] = cycles per kernel phase,
  *                   [16..23] / [24..31] = cycles / calls of selected device operations (tuning)
+ *   ready_dev       int32 device scalar or NULL. Streamed input: the kernel may be launched
+ *                   while the logits are still being copied in utterance order on ANOTHER
+ *                   stream, ready_chunk utterances at a time; after each chunk the copier stores
+ *                   the number of utterances delivered so far into *ready_dev (a 4-byte copy on
+ *                   the same copy stream). A thread group waits for its utterance's chunk. With
+ *                   a ready counter, order_dev must list chunk 0's utterances first, then chunk
+ *                   1's, ... (any order inside a chunk).
  * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
                               const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V,
@@ -107,7 +115,7 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
                               int32_t prune_history, int32_t input_mode, int32_t n_best,
                               int32_t* out_n_beams_dev, double* out_logit_score_dev, double* out_lm_score_dev,
                               uint8_t* out_tokens_dev, int32_t* out_lens_dev, int32_t* out_status_dev,
-                              uint64_t* stats_dev, void* stream);
+                              uint64_t* stats_dev, const int32_t* ready_dev, int32_t ready_chunk, void* stream);
 
 /* -------------------------------------------------------------------- greedy (A3/A4) */
 

@@ -90,6 +90,9 @@ int hs_score_sentence(void* h, const uint32_t* cps, const int64_t* word_off, int
   return 0;
 }
 
+// numpy-order float32 pairwise sum (the kernel's input classification), for a direct check
+float hs_pairwise_sum(const float* a, int n) { return np_pairwise_sum(a, n); }
+
 }  // extern "C"
 
 template <int NT, int BW, int OUTC>
@@ -112,6 +115,8 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
   sc.node_parent = node_parent.data();
   sc.node_info = node_info.data();
+  std::vector<float> rowsum((size_t)(T > 0 ? T : 1) * 9 + 16);
+  sc.rowsum = rowsum.data();
   sc.bnd = bnd.data();
   sc.outs_g.key = g_key.data();
   sc.outs_g.logit = g_logit.data();
@@ -125,7 +130,6 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
     UttIO io;
     io.logits = logits;
     io.T = T;
-    io.is_prob = is_prob;
     io.out_n = out_n;
     io.out_logit = out_logit;
     io.out_comb = out_comb;

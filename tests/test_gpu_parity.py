@@ -330,6 +330,40 @@ def test_full_size_properties(gpu_decoder, torch_cuda, cache_dir, rng):
     assert (np.diff(full.lm_score, axis=1)[np.arange(100)[None, 1:] < full.n_beams[:, None]] <= 0).all()
 
 
+def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, torch_cuda, cache_dir, rng):
+    """Pinned host logits take the single-launch streamed path (chunks + ready counter): same
+    beams as the device-resident launch, ragged last chunk included; and the probabilities-
+    vs-logits detection is per utterance inside the kernel (a mixed batch)."""
+    import math
+
+    from coral_b200 import decoder as dmod, synth
+
+    torch = torch_cuda
+    w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
+    idx = np.concatenate([rng.permutation(256) for _ in range(5)])[: 2 * dmod.H2D_CHUNK + 173]
+    lg = torch.from_numpy(w.logits[idx]).pin_memory()
+    ln = w.lengths[idx]
+    resident = gpu_decoder.decode_padded(lg.cuda(), ln, n_best=3)
+    for _ in range(2):
+        streamed = gpu_decoder.decode_padded(lg, ln, n_best=3)
+        for k in ("n_beams", "tokens", "lens"):
+            assert np.array_equal(getattr(streamed, k), getattr(resident, k)), k
+        valid = np.arange(3)[None, :] < resident.n_beams[:, None]  # score slots past n_beams are not written
+        for k in ("logit_score", "lm_score"):
+            assert np.array_equal(getattr(streamed, k)[valid], getattr(resident, k)[valid]), k
+    # mixed batch: every third utterance as probabilities
+    mixed = [w.logits[u, : w.lengths[u]] for u in range(12)]
+    for u in range(0, 12, 3):
+        z = mixed[u].astype(np.float64)
+        p = np.exp(z - z.max(axis=1, keepdims=True))
+        p = (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+        if math.isclose(float(p.sum(axis=1).mean()), 1):
+            mixed[u] = p
+    got = gpu_decoder.decode_beams_batch(None, mixed)
+    for x, g in zip(mixed, got):
+        beams_equal(oracle_decoder.decode_beams(x), g)
+
+
 # ------------------------------------------------------------------- golden fixtures on GPU
 def _golden(name):
     import json

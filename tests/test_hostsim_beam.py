@@ -146,3 +146,22 @@ def test_work_counters_match_oracle(sim, oracle_decoder, small_workload):
     st = sim.last_stats
     assert int(st[0]) == d["extensions"] and int(st[3]) == d["frames"]
     assert d["n_score"] <= int(st[1]) <= 2 * d["n_score"]
+
+
+def test_pairwise_sum_is_numpys_float32_order(rng):
+    """The kernel's probabilities-vs-logits test replays np.add.reduce's float32 summation
+    order (pyctcdecode: logits.sum(axis=1).mean()); checked bit for bit across the leaf,
+    remainder and recursive-split regimes."""
+    import ctypes as C
+
+    from hostsim_lib import build
+
+    lib = C.CDLL(build())
+    lib.hs_pairwise_sum.restype = C.c_float
+    lib.hs_pairwise_sum.argtypes = [C.c_void_p, C.c_int]
+    for n in list(range(0, 140)) + [255, 256, 257, 499, 500, 1000, 1023, 1500, 4097]:
+        for scale in (1.0, 1e-3):
+            a = (rng.standard_normal(n) * 50 * scale + scale).astype(np.float32)
+            want = np.add.reduce(a) if n else np.float32(0)
+            got = lib.hs_pairwise_sum(a.ctypes.data, n)
+            assert np.float32(got) == np.float32(want), (n, got, want)
