@@ -624,6 +624,11 @@ struct BeamDecoder {
     const uint32_t at = atom_add(&sm.n_out[q], 1u);
     const unsigned long long k = ordered_u64(comb);
     const uint32_t info = rb | (c << 16) | (kf << 24);
+    // counting-sort histogram for phase 3 (over every candidate: the overflow path finds its
+    // cut bucket from the same counts)
+    const uint32_t b = bucket_of(sm.mhat, scale, comb);
+    const uint32_t pos = atom_add(&sm.bcnt[b], 1u);
+    atom_add(&sm.gcnt[b >> 3], 1u);
     if (at < (uint32_t)OUTC) {
       sm.o_key[at] = k;
       sm.o_logit[at] = logit;
@@ -631,11 +636,8 @@ struct BeamDecoder {
       sm.o_aux[at] = aux;
       sm.o_child[at] = child;
       sm.o_info[at] = info;
-      // counting-sort histogram for phase 3
-      const uint32_t b = bucket_of(sm.mhat, scale, comb);
-      sm.o_pos[at] = (uint16_t)atom_add(&sm.bcnt[b], 1u);
+      sm.o_pos[at] = (uint16_t)pos;
       sm.o_bkt[at] = (uint8_t)b;
-      atom_add(&sm.gcnt[b >> 3], 1u);
     } else if (at < g_cap) {
       g.key[at] = k;
       g.logit[at] = logit;
@@ -813,8 +815,11 @@ struct BeamDecoder {
   }
 
   // ---- overflow path: more candidates than the shared-memory arrays hold ------------------
-  // Radix-select the beam_width best keys in HBM, then pull the winners into shared memory
-  // so that phase 3 ranks them exactly like the common case. `thr` = prune threshold key.
+  // Every candidate was counted into its score bucket while it was produced, so the bucket that
+  // holds the beam_width-th best score is known: the candidates of the buckets up to that one
+  // are pulled from HBM into shared memory (one pass) and phase 3 ranks them exactly as in the
+  // common case. Only if those buckets hold more than the shared arrays (scores bunched in one
+  // bucket) a radix select over the 64-bit keys picks the beam_width best. `thr` = prune key.
   static CORAL_DEV_OUTLINE void select_overflow(Sm& sm, const DecodeParams& P, const OutView& g, int q,
                                         unsigned long long thr) {
     const uint32_t n = sm.n_out[q];
@@ -823,8 +828,44 @@ struct BeamDecoder {
         g.key[i] = sm.o_key[i]; g.logit[i] = sm.o_logit[i]; g.order[i] = sm.o_order[i];
         g.aux[i] = sm.o_aux[i]; g.child[i] = sm.o_child[i]; g.info[i] = sm.o_info[i];
       }
+      if (lane == 0) {
+        uint32_t cum = 0;
+        int b = 0;
+        for (; b < kNB - 1; ++b) { cum += sm.bcnt[b]; if (cum >= (uint32_t)P.beam_width) break; }
+        if (b == kNB - 1) cum += sm.bcnt[b];
+        sm.sel_cut = (uint32_t)b;
+        sm.sel_eq = cum;  // candidates in the buckets up to the cut
+        sm.sel_n = 0;
+      }
     }
     CORAL_GSYNC(NT);
+    if (sm.sel_eq > (uint32_t)OUTC) { select_overflow_radix(sm, P, g, q, thr); return; }
+    const uint32_t cutb = sm.sel_cut;
+    const double scale = bucket_scale(P);
+    CORAL_LANES(NT) {
+      for (uint32_t base = lane; base < n; base += 4 * NT) {
+        unsigned long long k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t i = base + u * NT; k[u] = i < n ? g.key[i] : 0ULL; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = base + u * NT;
+          if (i >= n || k[u] < thr) continue;
+          if (bucket_of(sm.mhat, scale, key_to_double(k[u])) > cutb) continue;
+          const uint32_t at = atom_add(&sm.sel_n, 1u);  // < OUTC: at most sel_eq candidates qualify
+          sm.o_key[at] = k[u]; sm.o_logit[at] = g.logit[i]; sm.o_order[at] = g.order[i]; sm.o_aux[at] = g.aux[i];
+          sm.o_child[at] = g.child[i]; sm.o_info[at] = g.info[i];
+        }
+      }
+    }
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) { if (lane == 0) sm.n_out[q] = sm.sel_n; }
+    CORAL_GSYNC(NT);
+  }
+  static CORAL_DEV_OUTLINE void select_overflow_radix(Sm& sm, const DecodeParams& P, const OutView& g, int q,
+                                              unsigned long long thr) {
+    const uint32_t n = sm.n_out[q];
+    CORAL_LANES(NT) { if (lane == 0) sm.cnt[7] += 1u; }  // counter: frames that needed the radix select
     uint32_t* hist = reinterpret_cast<uint32_t*>(sm.o_key);  // 256 bins; o_key is free until the pull
     CORAL_LANES(NT) { if (lane == 0) { sm.sel_prefix = 0; sm.sel_mask = 0; sm.sel_need = (uint32_t)P.beam_width; sm.sel_n = 0; } }
     CORAL_GSYNC(NT);

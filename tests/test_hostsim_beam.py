@@ -80,6 +80,18 @@ def test_flat_logits_overflow_and_trim(sim, oracle_decoder, rng):
     _check(oracle_decoder, sim, flat[:30], beam_width=300, token_min_logp=-3.0, variant=2)
 
 
+def test_bunched_and_tied_scores_take_the_radix_select(sim, oracle_decoder, rng):
+    """Scores bunched into one ranking bucket (near-constant logits) overflow the shared
+    candidate arrays even after the bucket cut, so the 64-bit radix select runs; exactly
+    constant logits add bit-for-bit ties at the cut (earlier candidate wins)."""
+    near = (rng.standard_normal((14, 46)) * 1e-3).astype(np.float32)
+    _check(oracle_decoder, sim, near)
+    assert sim.last_stats[7] > 0
+    _check(oracle_decoder, sim, np.zeros((8, 46), np.float32))
+    assert sim.last_stats[7] > 0
+    _check(oracle_decoder, sim, np.zeros((6, 46), np.float32), beam_width=16, variant=1)
+
+
 def test_long_flat_utterance_many_prefixes(sim, oracle_decoder, rng):
     """Thousands of distinct prefixes in one utterance (back-pointer arena, slot reuse)."""
     from coral_b200 import synth
