@@ -113,54 +113,100 @@ def make_pool(wl, n_procs):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions. In-process NVML (two
+    cheap queries per sample); `nvidia-smi -lms` as the fallback. The period is a
+    compromise: frequent polling of the driver measurably slows the kernels being timed."""
 
-    def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
+        self.rows = []  # (time, sm_mhz, max_mhz, reasons bitmask)
         self.gpu = gpu_index
+        self.period = float(os.environ.get("CORAL_BENCH_CLOCK_PERIOD_MS", period_s * 1e3)) / 1e3
+        self.proc = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        if self.period <= 0:
+            return
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.time(), sm, mx, rs))
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            self.source = "nvml"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms",
+                 str(max(20, int(self.period * 1e3))), "-i", str(self._physical_index())],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+
+            def read():
+                for line in self.proc.stdout:
+                    p = [x.strip() for x in line.split(",")]
+                    try:
+                        rs = sum(bit for (_, bit), v in zip(self.REASONS, p[3:7]) if v.lower().startswith("active"))
+                        self.rows.append((time.time(), float(p[1]), float(p[2]), rs))
+                    except Exception:
+                        continue
+
+            threading.Thread(target=read, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
     def stop(self, t_from=0.0, t_to=float("inf")):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ts, r in self.rows:
-            if not (t_from <= ts <= t_to):
-                continue
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        rows = [r for r in self.rows if t_from <= r[0] <= t_to]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": sorted(name for name, bit in self.REASONS if mask & bit), "samples": len(rows),
+                "source": getattr(self, "source", None), "period_ms": self.period * 1e3}
 
 
 # ------------------------------------------------------------------------ reference arm
@@ -345,6 +391,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     beam_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+    if rank == 0:
+        print("beam kernel ms per step: " + " ".join(f"{a.elapsed_time(b):.2f}" for a, b in kern_ms), file=sys.stderr)
     assert int(d_status.sum().item()) == 0
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -30,7 +30,7 @@ SIGNATURES = {
     "coral_decoder_set_params": (_i32, [_vp, _f64, _f64, _f64, _i32]),
     "coral_decoder_info": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "coral_ctc_beam_decode": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _i32,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "coral_ctc_greedy": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "coral_ctc_collapse": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "coral_edit_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),

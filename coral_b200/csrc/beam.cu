@@ -28,22 +28,25 @@ struct BeamLaunch {
   uint8_t* out_tokens;
   int32_t* out_len;
   int32_t* out_status;
+  int32_t* out_frames;      // [B, n_best, max_words, 2] or NULL
+  int32_t* out_nwords;      // [B, n_best]
+  int32_t max_words;
   unsigned long long* stats;
   uint8_t* scratch;
   unsigned long long slot_bytes;
-  uint32_t node_cap, bnd_cap, ch_size, outs_cap;
+  uint32_t node_cap, bnd_cap, ch_size, outs_cap, wf_cap;
   int32_t* work;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_cap, uint32_t ch_size,
-                                              uint32_t outs_cap, size_t off[7]) {
+                                              uint32_t outs_cap, uint32_t wf_cap, size_t off[7]) {
   size_t o = 0;
   off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
   off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
   off[2] = o; o = align16(o + (size_t)ch_size * 4);        // row sums of the utterance being classified [T_max]
-  off[3] = o;                                              // (unused)
+  off[3] = o; o = align16(o + (size_t)wf_cap * sizeof(FrameRec));  // word-frame records (0 without word frames)
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
   off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
   off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
@@ -54,29 +57,31 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
 // fetches the next from a global counter; `order` lets the host hand out long
 // utterances first so the tail of the batch is short.
 // minimum CTAs per SM the register allocation must allow: what shared memory permits
-template <int NT, int BW, int OUTC>
+template <int NT, int BW, int OUTC, bool FRAMES>
 constexpr int min_ctas() {
-  constexpr int by_smem = (int)(232448 / (sizeof(GroupShared<BW, OUTC>) + 1024));
+  constexpr int by_smem = (int)(232448 / (sizeof(GroupShared<BW, OUTC, FRAMES>) + 1024));
   constexpr int by_threads = 2048 / NT;
   constexpr int by_regs = 65536 / (NT * 64);  // never ask for fewer than 64 registers per thread
   constexpr int m = by_smem < by_threads ? by_smem : by_threads;
   return m < 1 ? 1 : (m < by_regs ? m : by_regs);
 }
 
-template <int NT, int BW, int OUTC>
-__global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
+template <int NT, int BW, int OUTC, bool FRAMES>
+__global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Dec = BeamDecoder<NT, BW, OUTC>;
+  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
   typename Dec::Sm& sm = *reinterpret_cast<typename Dec::Sm*>(smem_raw);
   const uint32_t slot = blockIdx.x;
   SlotScratch sc;
   {
     size_t off[7];
-    slot_layout(L.node_cap, L.bnd_cap, L.ch_size, L.outs_cap, off);
+    slot_layout(L.node_cap, L.bnd_cap, L.ch_size, L.outs_cap, L.wf_cap, off);
     uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
     sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
     sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
     sc.rowsum = reinterpret_cast<float*>(base + off[2]);
+    sc.wf = reinterpret_cast<FrameRec*>(base + off[3]);
+    sc.wf_cap = L.wf_cap;
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
     sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
     sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
@@ -125,17 +130,20 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC>()) beam_search_kern
     io.out_tokens = L.out_tokens + (size_t)u * L.P.n_best * L.P.T_max;
     io.out_len = L.out_len + (size_t)u * L.P.n_best;
     io.out_status = L.out_status + u;
+    io.out_frames = FRAMES ? L.out_frames + (size_t)u * L.P.n_best * L.max_words * 2 : nullptr;
+    io.out_nwords = FRAMES ? L.out_nwords + (size_t)u * L.P.n_best : nullptr;
+    io.max_words = L.max_words;
     io.stats = L.stats;
     Dec::decode(sm, L.lm, L.P, sc, io);
     group_sync<NT>();
   }
 }
 
-template <int NT, int BW, int OUTC>
+template <int NT, int BW, int OUTC, bool FRAMES = false>
 static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStream_t st) {
-  using Dec = BeamDecoder<NT, BW, OUTC>;
+  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
   const size_t smem = sizeof(typename Dec::Sm);
-  auto kern = beam_search_kernel<NT, BW, OUTC>;
+  auto kern = beam_search_kernel<NT, BW, OUTC, FRAMES>;
   CORAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -150,26 +158,30 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
   uint32_t ch_size = 9 * (uint32_t)T + 16;  // floats of row-sum scratch: [T] sums + [T][8] partials
   uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
+  uint32_t wf_cap = FRAMES ? (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu) : 0u;
   size_t off[7];
-  const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
+  const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
   size_t free_b = 0, total_b = 0;
   CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + dec->scratch_bytes) / 2);
   uint32_t n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(want, budget / slot_bytes));
   const bool fits = dec->d_scratch && dec->node_cap >= node_cap && dec->bnd_cap >= bnd_cap &&
-                    dec->ch_size >= ch_size && dec->outs_cap >= outs_cap && dec->n_slots >= n_slots;
+                    dec->ch_size >= ch_size && dec->outs_cap >= outs_cap && dec->wf_cap >= wf_cap &&
+                    dec->n_slots >= n_slots;
   if (fits) {
     // reuse the arena with the (larger) capacities it was laid out for
     node_cap = dec->node_cap;
     bnd_cap = dec->bnd_cap;
     ch_size = dec->ch_size;
     outs_cap = dec->outs_cap;
+    wf_cap = dec->wf_cap;
   } else {
     node_cap = std::max(node_cap, dec->node_cap);
     bnd_cap = std::max(bnd_cap, dec->bnd_cap);
     ch_size = std::max(ch_size, dec->ch_size);
     outs_cap = std::max(outs_cap, dec->outs_cap);
-    const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, off);
+    wf_cap = std::max(wf_cap, dec->wf_cap);
+    const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
     n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max(want, dec->n_slots), budget / sb));
     // wait for earlier launches that may still use the old arena, then rebuild it
     CORAL_CUDA_OK(cudaDeviceSynchronize());
@@ -188,6 +200,7 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
     dec->bnd_cap = bnd_cap;
     dec->ch_size = ch_size;
     dec->outs_cap = outs_cap;
+    dec->wf_cap = wf_cap;
   }
   if (!dec->d_work) CORAL_CUDA_OK(cudaMalloc(&dec->d_work, sizeof(int32_t)));
   CORAL_CUDA_OK(cudaMemsetAsync(dec->d_work, 0, sizeof(int32_t), st));
@@ -197,6 +210,7 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   L.bnd_cap = bnd_cap;
   L.ch_size = ch_size;
   L.outs_cap = outs_cap;
+  L.wf_cap = wf_cap;
   L.work = dec->d_work;
   const uint32_t grid = std::min<uint32_t>(dec->n_slots, std::max<uint32_t>(1, want));
   kern<<<grid, NT, smem, st>>>(L);
@@ -300,8 +314,11 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
                               int32_t input_mode, int32_t n_best, int32_t* out_n_beams_dev,
                               double* out_logit_score_dev, double* out_lm_score_dev, uint8_t* out_tokens_dev,
                               int32_t* out_lens_dev, int32_t* out_status_dev, uint64_t* stats_dev,
-                              const int32_t* ready_dev, int32_t ready_chunk, void* stream) {
+                              const int32_t* ready_dev, int32_t ready_chunk, int32_t* out_word_frames_dev,
+                              int32_t* out_word_counts_dev, int32_t max_words, void* stream) {
   if (!dec) return fail(CORAL_EARG, "coral_ctc_beam_decode: null decoder");
+  if ((out_word_frames_dev != nullptr) != (out_word_counts_dev != nullptr) || (out_word_frames_dev && max_words < 1))
+    return fail(CORAL_EARG, "word frames need both output buffers and max_words >= 1");
   if (ready_dev && ready_chunk < 1) return fail(CORAL_EARG, "ready_chunk must be >= 1 with a ready counter");
   if (B < 0 || T_max < 0) return fail(CORAL_EARG, "negative batch or frame count");
   if (V != dec->P.V)
@@ -345,6 +362,17 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.stats = reinterpret_cast<unsigned long long*>(stats_dev);
   L.ready = ready_dev;
   L.ready_chunk = ready_chunk > 0 ? ready_chunk : 1;
+  L.out_frames = out_word_frames_dev;
+  L.out_nwords = out_word_counts_dev;
+  L.max_words = max_words;
+
+  if (out_word_frames_dev) {  // the instantiation that also tracks pyctcdecode's word frames
+    if (beam_width <= 32) return launch_beam<32, 32, 128, true>(dec, L, B, st);
+    if (beam_width <= 64) return launch_beam<64, 64, 192, true>(dec, L, B, st);
+    if (beam_width <= 128) return launch_beam<128, 128, 320, true>(dec, L, B, st);
+    if (beam_width <= 256) return launch_beam<256, 256, 640, true>(dec, L, B, st);
+    return launch_beam<256, 512, 1280, true>(dec, L, B, st);
+  }
 
   // threads per utterance: CORAL_BEAM_NT overrides the default (tuning knob)
   int nt = 0;

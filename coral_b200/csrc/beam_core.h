@@ -152,7 +152,18 @@ struct OutView {
   uint32_t* info;   // source beam (16 bits) | token << 16 | kind/flags << 24
 };
 
+// One finished word of a beam's text: frames [start, end) and the record of the word before it.
+// pyctcdecode carries text_frames as a Python list per beam; beams share list prefixes, so
+// an append-only arena of back-linked records holds them all (index 0 = empty list).
+struct alignas(16) FrameRec {
+  uint32_t parent;
+  int32_t start, end;
+  uint32_t pad;
+};
+
 struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after utterance
+  FrameRec* wf;         // word-frame records (only with word frames enabled)
+  uint32_t wf_cap;
   uint32_t* node_parent;
   uint32_t* node_info;  // tok | bnd << 8
   BndRec* bnd;
@@ -170,6 +181,9 @@ struct UttIO {
   double* out_comb;     // [n_best]
   uint8_t* out_tokens;  // [n_best, T_max]
   int32_t* out_len;     // [n_best]
+  int32_t* out_frames;  // [n_best, max_words, 2] word frames (start, end) -- word-frame kernels only
+  int32_t* out_nwords;  // [n_best]
+  int32_t max_words;
   int32_t* out_status;  // scalar: 0 ok, -4 capacity
   // optional [16]: extensions, LM scorings, n-gram probes, frames, lexicon probes, back-pointer records,
   // LM boundary records, (unused); [8..15] cycles per phase (thread 0): hash, expand,
@@ -179,8 +193,20 @@ struct UttIO {
 
 constexpr int kNB = 64;             // score buckets over the prune window
 
-template <int BW, int OUTC>
+// per-beam word timing (pyctcdecode's part_frames and text_frames), present only in the
+// word-frame instantiation of the kernel
+template <int BW, bool FRAMES>
+struct WordFrames {
+  int32_t pf0[2][BW], pf1[2][BW];  // part_frames (start, end) of the open word, -1 = unset
+  uint32_t head[2][BW];            // last FrameRec of text_frames
+  uint32_t count;                  // records used in SlotScratch::wf
+};
+template <int BW>
+struct WordFrames<BW, false> {};
+
+template <int BW, int OUTC, bool FRAMES = false>
 struct GroupShared {
+  WordFrames<BW, FRAMES> wf;
   static constexpr int HS = BW <= 32 ? 64 : (BW <= 64 ? 128 : (BW <= 128 ? 256 : (BW <= 256 ? 512 : 1024)));  // >= 2 BW
   // beams, double buffered
   double logit[2][BW];
@@ -379,9 +405,31 @@ struct PhaseTimer {
   }
 };
 
-template <int NT, int BW, int OUTC>
+template <int NT, int BW, int OUTC, bool FRAMES = false>
 struct BeamDecoder {
-  using Sm = GroupShared<BW, OUTC>;
+  using Sm = GroupShared<BW, OUTC, FRAMES>;
+
+  // candidate descriptor: representative beam, the LAST member beam (pyctcdecode keeps the
+  // later candidate's tuple on a merge -- its frames), token, kind/flags
+  static CORAL_DEV uint32_t info_pack(uint32_t rb, uint32_t last, uint32_t c, uint32_t kf) {
+    if (FRAMES) return rb | (last << 9) | (c << 18) | (kf << 25);
+    return rb | (c << 16) | (kf << 24);
+  }
+  static CORAL_DEV uint32_t info_rb(uint32_t i) { return FRAMES ? (i & 0x1FFu) : (i & 0xFFFFu); }
+  static CORAL_DEV uint32_t info_last(uint32_t i) { return (i >> 9) & 0x1FFu; }
+  static CORAL_DEV uint32_t info_c(uint32_t i) { return FRAMES ? ((i >> 18) & 0x7Fu) : ((i >> 16) & 0xFFu); }
+  static CORAL_DEV uint32_t info_kf(uint32_t i) { return FRAMES ? (i >> 25) : (i >> 24); }
+  static CORAL_DEV uint32_t frame_append(Sm& sm, const SlotScratch& sc, uint32_t parent, int32_t a, int32_t b) {
+    if constexpr (FRAMES) {
+      const uint32_t id = atom_add(&sm.wf.count, 1u);
+      if (id >= sc.wf_cap) { sm.status = -4; return 0; }
+      FrameRec r;
+      r.parent = parent; r.start = a; r.end = b; r.pad = 0;
+      sc.wf[id] = r;
+      return id;
+    }
+    return 0;
+  }
   static constexpr int HS = Sm::HS;
 
   // ---- live-node hash (shared memory), keyed by the prefix hash ------------------------
@@ -620,10 +668,10 @@ struct BeamDecoder {
   // more than OUTC candidates (flat logits / very wide beams).
   static CORAL_DEV_OUTLINE void emit(Sm& sm, const OutView& g, uint32_t g_cap, int q, double scale, double comb,
                                      double logit, uint32_t order, uint32_t aux, uint32_t child, uint32_t rb,
-                                     uint32_t c, uint32_t kf, unsigned long long& lmax) {
+                                     uint32_t c, uint32_t kf, unsigned long long& lmax, uint32_t last) {
     const uint32_t at = atom_add(&sm.n_out[q], 1u);
     const unsigned long long k = ordered_u64(comb);
-    const uint32_t info = rb | (c << 16) | (kf << 24);
+    const uint32_t info = info_pack(rb, last, c, kf);
     // counting-sort histogram for phase 3 (over every candidate: the overflow path finds its
     // cut bucket from the same counts)
     const uint32_t b = bucket_of(sm.mhat, scale, comb);
@@ -709,7 +757,7 @@ struct BeamDecoder {
           if (nm == 0) return;
           const uint32_t first = merge_members(sm, cur, mem, nm, (double)sm.lp[f][c], logit);
           emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
-               (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax);
+               (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax, mem[nm - 1]);
           return;
         }
         const uint32_t k = i % K;
@@ -720,7 +768,7 @@ struct BeamDecoder {
           if (b1 != kNone16) mem[nm++] = b1;
           const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
           emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], partial_score(P, wlen_m, fl_m))), logit,
-               k * nb + first, 0u, 0u, rb, c, 0u, lmax);
+               k * nb + first, 0u, 0u, rb, c, 0u, lmax, mem[nm - 1]);
           return;
         }
         if ((int)c == P.space_id && wlen_m == 0) return;  // a space after a closed word never extends
@@ -739,7 +787,7 @@ struct BeamDecoder {
           emit(sm, outs, sc.outs_cap, q, bscale,
                d_add(logit, d_add(sm.lm_raw[cur][crb],
                                   partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])))),
-               logit, order, 0u, crb, rb, c, 1u, lmax);
+               logit, order, 0u, crb, rb, c, 1u, lmax, mem[nm - 1]);
         } else if ((int)c == P.space_id) {
           // a word closes: score it with the LM and keep the result in a boundary record
           // (what pyctcdecode caches under the new text in cached_lm_scores)
@@ -759,7 +807,7 @@ struct BeamDecoder {
             raw_new = nr.lm_raw;
             sc.bnd[bnd_new] = nr;
           }
-          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, 0u, rb, c, 3u, lmax);
+          emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(raw_new, 0.0)), logit, order, bnd_new, 0u, rb, c, 3u, lmax, mem[nm - 1]);
         } else {
           // a letter extends the partial word: roll the word hash, probe the lexicon
           uint32_t nfl = 0, nwid = 0;
@@ -785,7 +833,7 @@ struct BeamDecoder {
             ps = partial_score(P, wlen_m + P.label_ncp[c], nfl);
           }
           emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
-               2u | (nfl << 2), lmax);
+               2u | (nfl << 2), lmax, mem[nm - 1]);
         }
       }
     }
@@ -978,7 +1026,7 @@ struct BeamDecoder {
   }
   static CORAL_DEV void rank_and_commit(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
                                         int cur, int q, unsigned long long thr, bool final_pass,
-                                        PhaseTimer* pt = nullptr) {
+                                        PhaseTimer* pt = nullptr, int t = 0) {
     const int nxt = cur ^ 1;
     const uint32_t n = sm.n_out[q];
     CORAL_LANES(NT) {
@@ -1014,6 +1062,26 @@ struct BeamDecoder {
         if (r >= (uint32_t)P.beam_width) continue;
         atom_add(&sm.S[q], 1u);
         const double logit = sm.o_logit[i];
+        if constexpr (FRAMES) {
+          // word timing of the member pyctcdecode keeps (the later candidate), SURVEY A5 step 4
+          const uint32_t inf = sm.o_info[i];
+          const uint32_t L = info_last(inf), c = info_c(inf);
+          int32_t p0 = sm.wf.pf0[cur][L], p1 = sm.wf.pf1[cur][L];
+          uint32_t hd = sm.wf.head[cur][L];
+          if (final_pass) {
+            if (sm.wlen[cur][L] > 0) hd = frame_append(sm, sc, hd, p0, p1);
+          } else if ((int)c == P.blank_id) {
+          } else if (c == meta_lc(sm.meta[cur][L])) {
+            p1 = t + 1;
+          } else if ((int)c == P.space_id) {
+            if (sm.wlen[cur][L] > 0) hd = frame_append(sm, sc, hd, p0, p1);
+            p0 = p1 = -1;
+          } else {
+            if (p0 < 0) p0 = t;
+            p1 = t + 1;
+          }
+          sm.wf.pf0[nxt][r] = p0; sm.wf.pf1[nxt][r] = p1; sm.wf.head[nxt][r] = hd;
+        }
         if (final_pass) {
           const double comb = key_to_double(ki);
           sm.logit[nxt][r] = logit;
@@ -1022,7 +1090,7 @@ struct BeamDecoder {
           continue;
         }
         const uint32_t info = sm.o_info[i];
-        const uint32_t rb = info & 0xFFFFu, c = (info >> 16) & 0xFFu, kf = info >> 24;
+        const uint32_t rb = info_rb(info), c = info_c(info), kf = info_kf(info);
         const uint32_t kind = kf & 3u;
         const uint32_t lc = (int)c == P.blank_id ? kLcBlank : c;
         if (kind == 0 || kind == 1) {
@@ -1076,7 +1144,7 @@ struct BeamDecoder {
 
   // ---- one frame: 3 barriers on the common path ------------------------------------------------
   static CORAL_DEV void frame_step(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc,
-                                   const UttIO& io, int f, int cur, int q, uint32_t nb) {
+                                   const UttIO& io, int f, int cur, int q, uint32_t nb, int t) {
     PhaseTimer pt;
     pt.start(io.stats);
     hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]], &lm, &P, &sc, f);
@@ -1090,7 +1158,7 @@ struct BeamDecoder {
       rebucket(sm, P, q);
       pt.mark(10);
     }
-    rank_and_commit(sm, lm, P, sc, cur, q, thr, false, &pt);
+    rank_and_commit(sm, lm, P, sc, cur, q, thr, false, &pt, t);
   }
 
   // ---- end of utterance ------------------------------------------------------
@@ -1137,7 +1205,7 @@ struct BeamDecoder {
         }
         // text node: the open-word node itself, or the parent of a closed-word node
         emit(sm, outs, sc.outs_cap, q, bscale, comb, logit, first, 0u,
-             open_or_root ? sm.node[cur][rb] : sc.node_parent[sm.node[cur][rb]], rb, 0u, 0u, lmax);
+             open_or_root ? sm.node[cur][rb] : sc.node_parent[sm.node[cur][rb]], rb, 0u, 0u, lmax, last);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
@@ -1168,6 +1236,17 @@ struct BeamDecoder {
         }
         for (int a = 0, b = len - 1; a < b; ++a, --b) { const uint8_t t = dst[a]; dst[a] = dst[b]; dst[b] = t; }
         io.out_len[r] = len;
+        if constexpr (FRAMES) {
+          // text_frames of the final beam, oldest word first
+          int nw = 0;
+          for (uint32_t h = sm.wf.head[fin][r]; h != 0; h = sc.wf[h].parent) ++nw;
+          int32_t* fr = io.out_frames + (size_t)r * io.max_words * 2;
+          int w = nw - 1;
+          for (uint32_t h = sm.wf.head[fin][r]; h != 0; h = sc.wf[h].parent, --w) {
+            if (w < io.max_words) { fr[2 * w] = sc.wf[h].start; fr[2 * w + 1] = sc.wf[h].end; }
+          }
+          io.out_nwords[r] = nw < io.max_words ? nw : io.max_words;
+        }
       }
     }
     CORAL_GSYNC(NT);
@@ -1267,6 +1346,7 @@ struct BeamDecoder {
         sm.wid[0][0] = 0;
         sm.wlen[0][0] = 0;
         sm.meta[0][0] = meta_pack(kNoTok, kLcNone, 0u);
+        if constexpr (FRAMES) { sm.wf.pf0[0][0] = -1; sm.wf.pf1[0][0] = -1; sm.wf.head[0][0] = 0; sm.wf.count = 1; }
         sc.node_parent[0] = kNoNode;
         sc.node_info[0] = kNoTok;
         if (lm.present) {
@@ -1294,7 +1374,7 @@ struct BeamDecoder {
         ps.mark(15);
       }
       for (int f = 0; f < nf; ++f) {
-        frame_step(sm, lm, P, sc, io, f, cur, q, nb);
+        frame_step(sm, lm, P, sc, io, f, cur, q, nb, t0 + f);
         if (sm.status != 0) { failed = true; break; }
         nb = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
         cur ^= 1;

@@ -52,7 +52,9 @@ def _torch():
 class DecodedBatch:
     """Raw result of one batched launch (host numpy arrays)."""
 
-    def __init__(self, n_beams, logit, comb, tokens, lens, status, stats=None):
+    def __init__(self, n_beams, logit, comb, tokens, lens, status, stats=None, word_frames=None, word_counts=None):
+        self.word_frames = word_frames   # int32 [B, n_best, max_words, 2] or None
+        self.word_counts = word_counts   # int32 [B, n_best] or None
         self.n_beams = n_beams
         self.logit_score = logit
         self.lm_score = comb
@@ -162,11 +164,12 @@ class BeamSearchDecoderCTC:
     def decode_padded(self, logits, lengths, beam_width: int = DEFAULT_BEAM_WIDTH,
                       beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
                       prune_history: bool = False, n_best: int = 1, input_mode: int = 0,
-                      collect_stats: bool = False, to_host: bool = True):
+                      collect_stats: bool = False, to_host: bool = True, word_frames: bool = False):
         """Decode a padded batch ``[B, T_max, V]`` (torch CUDA/CPU tensor or numpy) in one launch.
 
         ``lengths`` int [B]. Returns :class:`DecodedBatch` (numpy) or, with
         ``to_host=False``, the tuple of device tensors (the launch stays asynchronous).
+        ``word_frames=True`` selects the kernel that also tracks pyctcdecode's text_frames.
         """
         torch = _torch()
         h = self._handle()
@@ -217,19 +220,21 @@ class BeamSearchDecoderCTC:
             chunk_id = torch.arange(B, device=dev, dtype=torch.int64) // H2D_CHUNK
             d_order = torch.argsort(chunk_id * (int(logits.shape[1]) + 1) - d_len.to(torch.int64)).to(torch.int32)
             self._keepalive = (logits, marks)  # host buffers stay alive until the copies ran
-            d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self.decode_launch(
                 d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats,
-                ready=(d_ready, H2D_CHUNK))
+                ready=(d_ready, H2D_CHUNK), word_frames=word_frames)
         else:
             d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
             d_order = torch.argsort(d_len, descending=True).to(torch.int32)
-            d_n, d_logit, d_comb, d_tok, d_lens, d_status = self.decode_launch(
-                d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats)
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self.decode_launch(
+                d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats,
+                word_frames=word_frames)
         if not to_host:
-            return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats
+            return (d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats, *wf)
         out = DecodedBatch(d_n.cpu().numpy(), d_logit.cpu().numpy(), d_comb.cpu().numpy(), d_tok.cpu().numpy(),
                            d_lens.cpu().numpy(), d_status.cpu().numpy(),
-                           d_stats.cpu().numpy() if d_stats is not None else None)
+                           d_stats.cpu().numpy() if d_stats is not None else None,
+                           *(t.cpu().numpy() for t in wf))
         if out.status.any():
             bad = np.nonzero(out.status)[0]
             raise _lib.CoralError(int(out.status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
@@ -237,7 +242,8 @@ class BeamSearchDecoderCTC:
 
     def decode_launch(self, d_logits, d_len, d_order, beam_width: int = DEFAULT_BEAM_WIDTH,
                       beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
-                      n_best: int = 1, input_mode: int = 0, d_stats=None, events=None, ready=None):
+                      n_best: int = 1, input_mode: int = 0, d_stats=None, events=None, ready=None,
+                      word_frames: bool = False):
         """Queue one batched decode on device-resident inputs (asynchronous). ``events`` =
         (start, end) ``torch.cuda.Event`` recorded around the library call on the launching stream.
         ``ready`` = (int32 device counter, chunk) for logits still arriving on another stream."""
@@ -252,6 +258,11 @@ class BeamSearchDecoderCTC:
         d_tok = torch.zeros((B, n_best, Tm), dtype=torch.uint8, device=dev)
         d_lens = torch.zeros((B, n_best), dtype=torch.int32, device=dev)
         d_status = torch.empty(B, dtype=torch.int32, device=dev)
+        d_wf = d_wn = None
+        max_words = (Tm + 1) // 2 + 1  # a word needs a letter frame and (all but the last) a space frame
+        if word_frames:
+            d_wf = torch.empty((B, n_best, max_words, 2), dtype=torch.int32, device=dev)
+            d_wn = torch.zeros((B, n_best), dtype=torch.int32, device=dev)
         if events is not None:
             events[0].record()
         _lib.check(_lib.load().coral_ctc_beam_decode(
@@ -260,9 +271,12 @@ class BeamSearchDecoderCTC:
             int(n_best), d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
             d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None,
             ready[0].data_ptr() if ready is not None else None, int(ready[1]) if ready is not None else 0,
+            d_wf.data_ptr() if word_frames else None, d_wn.data_ptr() if word_frames else None, max_words,
             _lib.stream_ptr(dev)))
         if events is not None:
             events[1].record()
+        if word_frames:
+            return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_wf, d_wn
         return d_n, d_logit, d_comb, d_tok, d_lens, d_status
 
     def device_tokens_to_text(self, d_tok, d_lens) -> list[str]:
@@ -337,20 +351,26 @@ class BeamSearchDecoderCTC:
         if not logits_list:
             return []
         buf, lengths = self._pad(logits_list)
-        out = self.decode_padded(buf, lengths, beam_width, beam_prune_logp, token_min_logp, prune_history,
-                                 n_best=n_best)
-        B, nb = out.lens.shape
-        texts = self.tokens_to_text(out.tokens.reshape(B * nb, -1), out.lens.reshape(-1))
+        n_best = max(1, min(int(n_best), int(beam_width)))
+        # bound the word-frame output buffer (B x n_best x max_words x 8 bytes) per launch
+        per_utt = n_best * ((buf.shape[1] + 1) // 2 + 1) * 8 + n_best * buf.shape[1]
+        step = max(1, min(len(logits_list), (1 << 30) // max(per_utt, 1)))
         res = []
-        for u in range(B):
-            beams = []
-            for r in range(min(int(out.n_beams[u]), nb)):
-                text = texts[u * nb + r]
-                # word time offsets are not tracked yet: frames are (-1, -1)
-                frames = [(w, (-1, -1)) for w in text.split()]
-                ls, cs = float(out.logit_score[u, r]), float(out.lm_score[u, r])
-                beams.append((text, frames, ls, cs) if mp_safe else (text, None, frames, ls, cs))
-            res.append(beams)
+        for a0 in range(0, len(logits_list), step):
+            out = self.decode_padded(buf[a0:a0 + step], lengths[a0:a0 + step], beam_width, beam_prune_logp,
+                                     token_min_logp, prune_history, n_best=n_best, word_frames=True)
+            B, nb = out.lens.shape
+            texts = self.tokens_to_text(out.tokens.reshape(B * nb, -1), out.lens.reshape(-1))
+            for u in range(B):
+                beams = []
+                for r in range(min(int(out.n_beams[u]), nb)):
+                    text = texts[u * nb + r]
+                    wf = out.word_frames[u, r, : out.word_counts[u, r]]
+                    # pyctcdecode: list(zip(text.split(), text_frames))
+                    frames = list(zip(text.split(), ((int(x), int(y)) for x, y in wf)))
+                    ls, cs = float(out.logit_score[u, r]), float(out.lm_score[u, r])
+                    beams.append((text, frames, ls, cs) if mp_safe else (text, None, frames, ls, cs))
+                res.append(beams)
         return res
 
     def decode(self, logits, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,

@@ -108,6 +108,11 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *                   the same copy stream). A thread group waits for its utterance's chunk. With
  *                   a ready counter, order_dev must list chunk 0's utterances first, then chunk
  *                   1's, ... (any order inside a chunk).
+ *   out_word_frames_dev  int32 [B, n_best, max_words, 2] or NULL: pyctcdecode's text_frames, the
+ *                   (start, end) frame of every word of each returned beam (what HF turns into
+ *                   word_offsets, HF:...processing_wav2vec2_with_lm.py:416-443); with it,
+ *   out_word_counts_dev  int32 [B, n_best] words written per beam. max_words >= (T_max + 1) / 2 + 1
+ *                   holds every possible transcript. NULL selects the kernel without word timing.
  * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
                               const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V,
@@ -115,7 +120,9 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
                               int32_t prune_history, int32_t input_mode, int32_t n_best,
                               int32_t* out_n_beams_dev, double* out_logit_score_dev, double* out_lm_score_dev,
                               uint8_t* out_tokens_dev, int32_t* out_lens_dev, int32_t* out_status_dev,
-                              uint64_t* stats_dev, const int32_t* ready_dev, int32_t ready_chunk, void* stream);
+                              uint64_t* stats_dev, const int32_t* ready_dev, int32_t ready_chunk,
+                              int32_t* out_word_frames_dev, int32_t* out_word_counts_dev, int32_t max_words,
+                              void* stream);
 
 /* -------------------------------------------------------------------- greedy (A3/A4) */
 

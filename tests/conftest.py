@@ -59,6 +59,10 @@ def beams_equal(ref_beams, got_beams, rel=1e-4):
         assert r[0] == g[0], f"beam {i}: {r[0]!r} != {g[0]!r}"
         assert abs(r[-2] - g[-2]) <= rel * max(1.0, abs(r[-2])), (i, r[-2], g[-2])
         assert abs(r[-1] - g[-1]) <= rel * max(1.0, abs(r[-1])), (i, r[-1], g[-1])
+        if len(g) >= 4:  # word frames travel with the beam: (word, (start_frame, end_frame))
+            rf = [(w, (int(a), int(b))) for w, (a, b) in r[2]]
+            gf = [(w, (int(a), int(b))) for w, (a, b) in g[-3]]
+            assert rf == gf, f"beam {i} ({r[0]!r}): word frames {rf} != {gf}"
 
 
 @pytest.fixture(scope="session")

@@ -95,11 +95,17 @@ float hs_pairwise_sum(const float* a, int n) { return np_pairwise_sum(a, n); }
 
 }  // extern "C"
 
-template <int NT, int BW, int OUTC>
-static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, int is_prob, int32_t* out_n,
-               double* out_logit, double* out_comb, uint8_t* out_tokens, int32_t* out_len,
-               unsigned long long* stats, int n_utt_repeat) {
-  using Dec = BeamDecoder<NT, BW, OUTC>;
+struct FrameOut {
+  int32_t* frames;
+  int32_t* nwords;
+  int32_t max_words;
+};
+
+template <int NT, int BW, int OUTC, bool FRAMES>
+static int run_t(HsDecoder* d, const DecodeParams& P, const float* logits, int T, int is_prob, int32_t* out_n,
+                 double* out_logit, double* out_comb, uint8_t* out_tokens, int32_t* out_len,
+                 unsigned long long* stats, int n_utt_repeat, FrameOut fo) {
+  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
   typename Dec::Sm* sm = new typename Dec::Sm();
   LmView lm;
   memset(&lm, 0, sizeof(lm));
@@ -113,6 +119,9 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
   std::vector<unsigned long long> g_key(sc.outs_cap);
   std::vector<double> g_logit(sc.outs_cap);
   std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
+  std::vector<FrameRec> wf(FRAMES ? sc.node_cap : 1);
+  sc.wf = wf.data();
+  sc.wf_cap = (uint32_t)wf.size();
   sc.node_parent = node_parent.data();
   sc.node_info = node_info.data();
   std::vector<float> rowsum((size_t)(T > 0 ? T : 1) * 9 + 16);
@@ -136,11 +145,22 @@ static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, 
     io.out_tokens = out_tokens;
     io.out_len = out_len;
     io.out_status = &status;
+    io.out_frames = fo.frames;
+    io.out_nwords = fo.nwords;
+    io.max_words = fo.max_words;
     io.stats = rep == 0 ? stats : nullptr;
     Dec::decode(*sm, lm, P, sc, io);
   }
   delete sm;
   return status;
+}
+
+template <int NT, int BW, int OUTC>
+static int run(HsDecoder* d, const DecodeParams& P, const float* logits, int T, int is_prob, int32_t* out_n,
+               double* out_logit, double* out_comb, uint8_t* out_tokens, int32_t* out_len,
+               unsigned long long* stats, int n_utt_repeat, FrameOut fo) {
+  if (fo.frames) return run_t<NT, BW, OUTC, true>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, n_utt_repeat, fo);
+  return run_t<NT, BW, OUTC, false>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, n_utt_repeat, fo);
 }
 
 extern "C" {
@@ -149,8 +169,9 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
               double token_min_logp, double alpha, double beta, double unk_score_offset, int score_boundary,
               double log_base_change, int input_mode, int n_best, int variant, int repeat, int32_t* out_n,
               double* out_logit, double* out_comb, uint8_t* out_tokens, int32_t* out_len,
-              unsigned long long* stats) {
+              unsigned long long* stats, int32_t* out_frames, int32_t* out_nwords, int32_t max_words) {
   HsDecoder* d = (HsDecoder*)h;
+  const FrameOut fo{out_frames, out_nwords, max_words};
   DecodeParams P = d->P;
   P.beam_width = beam_width;
   P.n_best = n_best;
@@ -164,10 +185,10 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
   P.unk_score_offset = unk_score_offset;
   P.log_base_change = log_base_change;
   switch (variant) {
-    case 0: if (beam_width > 128) break; return run<32, 128, 256>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
-    case 1: if (beam_width > 32) break; return run<32, 32, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
-    case 2: if (beam_width > 512) break; return run<128, 512, 1024>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
-    case 3: if (beam_width > 128) break; return run<64, 128, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat);
+    case 0: if (beam_width > 128) break; return run<32, 128, 256>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 1: if (beam_width > 32) break; return run<32, 32, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 2: if (beam_width > 512) break; return run<128, 512, 1024>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 3: if (beam_width > 128) break; return run<64, 128, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     default: break;
   }
   g_err = "unsupported variant / beam width";

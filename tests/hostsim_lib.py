@@ -81,7 +81,7 @@ class HostSim:
 
     def decode_beams(self, logits, beam_width=100, beam_prune_logp=-10.0, token_min_logp=-5.0, alpha=0.5,
                      beta=1.5, unk_score_offset=-10.0, score_boundary=True, input_mode=0, is_prob=None,
-                     variant=0, repeat=1, n_best=None):
+                     variant=0, repeat=1, n_best=None, frames=False):
         logits = np.ascontiguousarray(logits, dtype=np.float32)
         T, V = logits.shape
         if is_prob is None:
@@ -98,18 +98,26 @@ class HostSim:
         self.lib.hs_decode.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
             C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        max_words = (Tm + 1) // 2 + 1
+        out_frames = np.full((n_best, max_words, 2), -7, np.int32) if frames else None
+        out_nwords = np.zeros(n_best, np.int32) if frames else None
         st = self.lib.hs_decode(
             self.h, logits.ctypes.data, T, int(is_prob), beam_width, beam_prune_logp, token_min_logp, alpha, beta,
             unk_score_offset, int(score_boundary), LOG_BASE_CHANGE, input_mode, n_best, variant, repeat,
             out_n.ctypes.data, out_logit.ctypes.data, out_comb.ctypes.data, out_tok.ctypes.data,
-            out_len.ctypes.data, stats.ctypes.data)
+            out_len.ctypes.data, stats.ctypes.data,
+            out_frames.ctypes.data if frames else None, out_nwords.ctypes.data if frames else None, max_words)
         if st != 0:
             raise RuntimeError(f"hostsim status {st}: {self.lib.hs_last_error().decode()}")
         beams = []
         for r in range(min(int(out_n[0]), n_best)):
             text = "".join(self.labels[t] for t in out_tok[r, : out_len[r]])
-            beams.append((text, float(out_logit[r]), float(out_comb[r])))
+            if frames:
+                fr = [(int(a), int(b)) for a, b in out_frames[r, : out_nwords[r]]]
+                beams.append((text, list(zip(text.split(), fr)), float(out_logit[r]), float(out_comb[r])))
+            else:
+                beams.append((text, float(out_logit[r]), float(out_comb[r])))
         self.last_stats = stats
         return beams
 

@@ -54,7 +54,7 @@ def test_argument_errors_map_to_the_reference_exceptions():
         _lib.check(lib.coral_edit_counts(None, None, None, None, 4, 1, 10, 0, None, None, None))
     with pytest.raises(ValueError):  # beam_width out of range is rejected before any CUDA call
         _lib.check(lib.coral_ctc_beam_decode(None, None, None, None, 1, 1, 46, 100, -10.0, -5.0, 0, 0, 1,
-                                             None, None, None, None, None, None, None, None, 0, None))
+                                             None, None, None, None, None, None, None, None, 0, None, None, 0, None))
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():

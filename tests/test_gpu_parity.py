@@ -304,6 +304,11 @@ def test_hf_processor_with_lm_drop_in(gpu_decoder, oracle_decoder, small_workloa
         assert abs(a - r[3]) <= 1e-4 * max(1, abs(r[3]))
     one = proc.decode(w.logits[0, : w.lengths[0]])
     assert one.text == ref[0][0]
+    # word offsets (HF:...processing_wav2vec2_with_lm.py:416-443) come from the decoder's text_frames
+    wo = proc.batch_decode(w.logits[:6], output_word_offsets=True)
+    for offs, r in zip(wo.word_offsets, ref):
+        assert [(d["word"], (d["start_offset"], d["end_offset"])) for d in offs] == \
+               [(wd, (int(a), int(b))) for wd, (a, b) in r[2]]
     # round trip through pyctcdecode's directory layout
     proc.save_pretrained(str(tmp_path / "m"))
     assert (tmp_path / "m" / "alphabet.json").exists() and (tmp_path / "m" / "language_model" / "attrs.json").exists()

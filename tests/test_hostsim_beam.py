@@ -92,6 +92,29 @@ def test_bunched_and_tied_scores_take_the_radix_select(sim, oracle_decoder, rng)
     _check(oracle_decoder, sim, np.zeros((6, 46), np.float32), beam_width=16, variant=1)
 
 
+def test_word_frames_match_the_oracle(sim, oracle_decoder, small_workload, rng):
+    """text_frames of every final beam (pyctcdecode's word time offsets): peaky utterances,
+    flat logits (merges pick the later member's frames), trailing open word, leading space."""
+    from coral_b200 import synth
+
+    w = small_workload
+    cases = [w.logits[u, : w.lengths[u]] for u in range(5)] + [synth.flat_logits(40, rng), w.logits[0, :7],
+                                                                w.logits[1, :1], np.zeros((0, 46), np.float32)]
+    for lg in cases:
+        ref = oracle_decoder.decode_beams(lg)
+        for variant in (0, 3):
+            got = sim.decode_beams(lg, frames=True, variant=variant)
+            assert len(ref) == len(got)
+            for r, g in zip(ref, got):
+                assert r[0] == g[0]
+                assert [(wd, (int(a), int(b))) for wd, (a, b) in r[2]] == g[1], (r[0], r[2], g[1])
+    # the frames instantiation returns the same beams and scores as the plain one
+    lg = cases[0]
+    a = sim.decode_beams(lg)
+    b = sim.decode_beams(lg, frames=True)
+    assert [(x[0], x[1], x[2]) for x in a] == [(x[0], x[2], x[3]) for x in b]
+
+
 def test_long_flat_utterance_many_prefixes(sim, oracle_decoder, rng):
     """Thousands of distinct prefixes in one utterance (back-pointer arena, slot reuse)."""
     from coral_b200 import synth

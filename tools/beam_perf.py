@@ -44,3 +44,10 @@ if os.environ.get("CORAL_PHASES"):
     print("op latency (cycles/call, calls/frame): " + ", ".join(
         f"{n}={st[16+i]/max(st[24+i],1):.0f}x{st[24+i]/fr:.2f}" for i, n in enumerate(ops)))
     print(f"per frame: ext={st[0]/fr:.1f} lm_scorings={st[1]/fr:.2f} ngram_probes={st[2]/fr:.2f} lex_probes={st[4]/fr:.2f} nodes={st[5]/fr:.2f} radix_select_frames/utt={st[7]/a.utts:.2f}")
+if os.environ.get("CORAL_FRAMES"):
+    ts = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dec.decode_launch(d_logits, d_len, d_order, beam_width=a.beam, input_mode=a.mode, events=(e0, e1), word_frames=True)
+        torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print(f"with word frames: {float(np.median(ts)):.2f} ms (min {min(ts):.2f})")
