@@ -8,29 +8,50 @@
 // stays on the host (coral_b200/greedy.py).
 //
 // Roofline: the argmax kernel reads every logit once (T*V*4 bytes per
-// utterance) and writes T*4 bytes; nothing is re-read. A persistent grid streams tiles of
-// 128 frames through a two-stage cp.async pipeline in shared memory.
+// utterance) and writes T*4 bytes; nothing is re-read. Tiles of 128 frames are brought into
+// shared memory by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) issued by one
+// thread, so the other threads spend their instructions on the row scans only; about nine
+// CTAs per SM keep enough tiles in flight to cover the HBM latency.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace coral {
 
-constexpr int kTileFrames = 128;  // frames per pipeline stage (= threads per CTA)
+constexpr int kTileFrames = 128;  // frames per tile (= threads per CTA)
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
 }
 
-// Asynchronous copy of one tile (nfr * V contiguous floats) into a shared-memory stage, at
-// the widest granularity the source alignment allows (rows are 184 B: 8-byte aligned always,
-// 16-byte aligned for every other frame).
+// Fallback copy of one tile (n_floats contiguous floats) for the tiles a 16-byte-granular bulk
+// copy must not touch (it would read a few bytes outside the caller's buffer).
 __device__ __forceinline__ void issue_tile(const float* __restrict__ src, float* stage, int n_floats) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(src);
   if ((a & 15) == 0) {
@@ -45,109 +66,138 @@ __device__ __forceinline__ void issue_tile(const float* __restrict__ src, float*
     for (int e = threadIdx.x; e < n_floats; e += blockDim.x) cp_async4(stage + e, src + e);
   }
   asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// Persistent, double-buffered: while the CTA scans the rows of one tile, the next tile is in
-// flight (cp.async, no registers involved). Tiles are (utterance, 128-frame block); blocks
-// past an utterance's length are skipped. Thread f scans row f of the tile from shared memory.
+// numpy.argmax of one row in shared memory: first maximum wins, the first NaN beats everything.
+__device__ __forceinline__ int row_argmax(const float* row, int V, float& best_out) {
+  float best;
+  int id;
+  bool nan;
+  if ((V & 1) == 0 && (reinterpret_cast<uintptr_t>(row) & 7) == 0) {
+    // two independent chains over the even and the odd elements, 8-byte shared loads
+    const float2* r2 = reinterpret_cast<const float2*>(row);
+    float2 x = r2[0];
+    float ba = x.x, bb = x.y;
+    int ia = 0, ib = 1;
+    nan = (x.x != x.x) | (x.y != x.y);
+#pragma unroll 4
+    for (int v = 1; v < (V >> 1); ++v) {
+      x = r2[v];
+      nan |= (x.x != x.x) | (x.y != x.y);
+      if (x.x > ba) { ba = x.x; ia = 2 * v; }
+      if (x.y > bb) { bb = x.y; ib = 2 * v + 1; }
+    }
+    const bool take_b = bb > ba || (bb == ba && ib < ia);
+    best = take_b ? bb : ba;
+    id = take_b ? ib : ia;
+  } else {
+    best = row[0];
+    id = 0;
+    nan = best != best;
+#pragma unroll 4
+    for (int v = 1; v < V; ++v) {
+      const float x = row[v];
+      nan |= x != x;
+      if (x > best) { best = x; id = v; }
+    }
+  }
+  if (nan) {  // rare: numpy returns the first NaN
+    for (int v = 0; v < V; ++v)
+      if (row[v] != row[v]) { best = row[v]; id = v; break; }
+  }
+  best_out = best;
+  return id;
+}
+
+// Persistent grid over (utterance, 128-frame block) tiles; blocks past an utterance's length
+// are skipped. Thread f scans row f of the tile from shared memory.
 __global__ void __launch_bounds__(kTileFrames)
 ctc_argmax_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lengths, int B, int T_max, int V,
                   int blank_id, int pad_fixup, int32_t* __restrict__ out_ids) {
-  extern __shared__ __align__(16) float smem[];
-  const int stage_floats = (kTileFrames * V + 3) & ~3;
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ __align__(8) unsigned long long bar;
   const int tpu = (T_max + kTileFrames - 1) / kTileFrames;
   const long long n_tiles = (long long)B * tpu;
-  auto tile_frames = [&](long long tile, int& u, int& t0) -> int {
-    u = (int)(tile / tpu);
-    t0 = (int)(tile % tpu) * kTileFrames;
+  const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(logits);
+  const uintptr_t buf_hi = buf_lo + (size_t)B * T_max * V * sizeof(float);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  unsigned phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int u = (int)(tile / tpu);
+    const int t0 = (int)(tile % tpu) * kTileFrames;
     const int T = lengths ? lengths[u] : T_max;
-    return T - t0 < kTileFrames ? T - t0 : kTileFrames;  // <= 0: nothing to do
-  };
-  auto next_valid = [&](long long tile) -> long long {
-    int u, t0;
-    while (tile < n_tiles && tile_frames(tile, u, t0) <= 0) tile += gridDim.x;
-    return tile;
-  };
-  long long cur = next_valid(blockIdx.x);
-  int st = 0;
-  if (cur < n_tiles) {
-    int u, t0;
-    const int nfr = tile_frames(cur, u, t0);
-    issue_tile(logits + ((size_t)u * T_max + t0) * V, smem, nfr * V);
-  }
-  while (cur < n_tiles) {
-    const long long nxt = next_valid(cur + gridDim.x);
-    if (nxt < n_tiles) {
-      int u, t0;
-      const int nfr = tile_frames(nxt, u, t0);
-      issue_tile(logits + ((size_t)u * T_max + t0) * V, smem + (st ^ 1) * stage_floats, nfr * V);
-      asm volatile("cp.async.wait_group 1;");
+    const int nfr = T - t0 < kTileFrames ? T - t0 : kTileFrames;
+    if (nfr <= 0) continue;  // uniform
+    const float* src = logits + ((size_t)u * T_max + t0) * V;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uintptr_t a0 = a & ~(uintptr_t)15;
+    unsigned lead = (unsigned)(a - a0);
+    const unsigned bytes = (lead + (unsigned)nfr * V * 4u + 15u) & ~15u;
+    if (a0 >= buf_lo && a0 + bytes <= buf_hi) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(stage, reinterpret_cast<const void*>(a0), bytes, &bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
     } else {
-      asm volatile("cp.async.wait_group 0;");
+      lead = 0;
+      issue_tile(src, reinterpret_cast<float*>(stage), nfr * V);
+      __syncthreads();
     }
-    __syncthreads();
-    int u, t0;
-    const int nfr = tile_frames(cur, u, t0);
     const int f = threadIdx.x;
     if (f < nfr) {
-      const float* row = smem + st * stage_floats + f * V;
-      float best = row[0];
-      int id = 0;
-      bool all_m100 = best == -100.0f;
-      for (int v = 1; v < V; ++v) {
-        const float x = row[v];
-        all_m100 &= x == -100.0f;
-        // first maximum wins; like numpy, the first NaN wins over everything
-        if (x > best || (x != x && best == best)) { best = x; id = v; }
+      const float* row = reinterpret_cast<const float*>(stage + lead) + (size_t)f * V;
+      float best;
+      int id = row_argmax(row, V, best);
+      if (pad_fixup && best == -100.0f) {  // "all -100 row -> pad" (R:src/coral/compute_metrics.py:66)
+        bool all_m100 = true;
+        for (int v = 0; v < V; ++v) all_m100 &= row[v] == -100.0f;
+        if (all_m100) id = blank_id;
       }
-      if (pad_fixup && all_m100) id = blank_id;
       out_ids[(size_t)u * T_max + t0 + f] = id;
     }
-    __syncthreads();  // the stage is free again before the next iteration refills it
-    cur = nxt;
-    st ^= 1;
+    __syncthreads();  // every row was read before the next tile overwrites the stage
   }
 }
 
-// One CTA per utterance: keep[t] = id != blank && (!group || t == 0 || id != ids[t-1]),
-// compacted with a block scan. Safe in place (writes never pass the read cursor).
-__global__ void __launch_bounds__(256)
-ctc_collapse_kernel(const int32_t* ids, const int32_t* __restrict__ lengths, int T_max, int blank_id,
+// One warp per utterance: keep[t] = id != blank && (!group || t == 0 || id != ids[t-1]),
+// compacted with ballots (no block barriers). Safe in place: a chunk is loaded completely
+// before anything is stored, and stores never pass the read cursor.
+constexpr int kCollapseWarps = 8;
+__global__ void __launch_bounds__(kCollapseWarps * 32)
+ctc_collapse_kernel(const int32_t* ids, const int32_t* __restrict__ lengths, int B, int T_max, int blank_id,
                     int group_tokens, int32_t* out_tokens, int32_t* __restrict__ out_lens) {
-  __shared__ int warp_tot[8];
-  __shared__ int base_s;
-  const int u = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x * kCollapseWarps + (threadIdx.x >> 5);
+  if (u >= B) return;
   const int T = lengths ? lengths[u] : T_max;
   const int32_t* src = ids + (size_t)u * T_max;
   int32_t* dst = out_tokens + (size_t)u * T_max;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base_s = 0;
-  __syncthreads();
-  for (int c0 = 0; c0 < T; c0 += 256) {
-    const int t = c0 + threadIdx.x;
-    int id = 0, keep = 0;
-    if (t < T) {
-      id = src[t];
-      const int prev = (t > 0) ? src[t - 1] : -1;
-      keep = (id != blank_id) && (!group_tokens || t == 0 || id != prev);
+  int base = 0;
+  int carry = -1;  // id of the frame before the current chunk
+  for (int c0 = 0; c0 < T; c0 += 128) {
+    int id[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = c0 + 32 * k + lane;
+      id[k] = t < T ? src[t] : blank_id;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    const int in_warp = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(m);
-    __syncthreads();  // all reads of this chunk are done, warp totals visible
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
-    const int base = base_s;
-    if (keep) dst[base + woff + in_warp] = id;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < 8; ++w) tot += warp_tot[w];
-      base_s = base + tot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = c0 + 32 * k + lane;
+      int prev = __shfl_up_sync(0xffffffffu, id[k], 1);
+      if (lane == 0) prev = carry;
+      const bool keep = t < T && id[k] != blank_id && (!group_tokens || t == 0 || id[k] != prev);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) dst[base + __popc(m & ((1u << lane) - 1u))] = id[k];
+      base += __popc(m);
+      carry = __shfl_sync(0xffffffffu, id[k], 31);
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) out_lens[u] = base_s;
+  if (lane == 0) out_lens[u] = base;
 }
 
 }  // namespace coral
@@ -162,8 +212,9 @@ int32_t coral_ctc_collapse(const int32_t* ids_dev, const int32_t* lengths_dev, i
   if (B < 0 || T_max < 0) return fail(CORAL_EARG, "negative batch or frame count");
   if (B == 0) return CORAL_OK;
   if (!ids_dev || !out_tokens_dev || !out_lens_dev) return fail(CORAL_EARG, "coral_ctc_collapse: null buffer");
-  ctc_collapse_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(ids_dev, lengths_dev, T_max, blank_id,
-                                                                    group_tokens, out_tokens_dev, out_lens_dev);
+  ctc_collapse_kernel<<<(unsigned)((B + kCollapseWarps - 1) / kCollapseWarps), kCollapseWarps * 32, 0,
+                        (cudaStream_t)stream>>>(ids_dev, lengths_dev, B, T_max, blank_id, group_tokens, out_tokens_dev,
+                                                out_lens_dev);
   CORAL_CUDA_OK(cudaGetLastError());
   return CORAL_OK;
 }
@@ -177,8 +228,7 @@ int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, in
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* ids = out_ids_dev ? out_ids_dev : out_tokens_dev;
   if (T_max > 0) {
-    const size_t stage_floats = ((size_t)kTileFrames * V + 3) & ~(size_t)3;
-    const size_t smem = 2 * stage_floats * sizeof(float);
+    const size_t smem = (((size_t)kTileFrames * V * sizeof(float) + 15) & ~(size_t)15) + 32;
     if (smem > 200 * 1024) return fail(CORAL_EARG, "vocabulary too large for the greedy kernel's tiles");
     CORAL_CUDA_OK(cudaFuncSetAttribute(ctc_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, per_sm = 0;

@@ -60,6 +60,46 @@ def test_greedy_matches_numpy_argmax_and_tokenizer_rules(torch_cuda, coral_vocab
         assert got[b] == ids_to_string(ref_ids[b, : lengths[b]])
 
 
+@pytest.mark.parametrize("V,T,offset", [(46, 300, 0), (46, 257, 2), (45, 129, 0), (7, 40, 1), (64, 128, 0)])
+def test_greedy_argmax_special_values_and_alignments(torch_cuda, rng, V, T, offset):
+    """np.argmax semantics on the awkward values (first NaN wins, -inf rows, +-0 ties, ties
+    between even and odd positions) for even and odd vocabularies, and for a logits buffer that
+    starts 4 * offset bytes off 16-byte alignment (the bulk-copy path must stay inside it)."""
+    from coral_b200 import _lib
+
+    torch = torch_cuda
+    B = 9
+    x = (rng.standard_normal((B, T, V)) * 3).astype(np.float32)
+    x[0, :, :] = -np.inf
+    x[1, ::3, 5 % V] = np.nan
+    x[1, ::6, 2 % V] = np.nan
+    x[2, :, :] = 0.0
+    x[2, ::2, 3 % V] = -0.0
+    x[3, :, 1] = x[3, :, 4 % V] = 50.0           # odd position ties with a later even one
+    x[4, :, 4 % V] = x[4, :, 1] = 50.0
+    x[5, 5:9, :] = -100.0                         # -100 rows -> pad when the fix-up is on
+    x[6, :, V - 1] = np.inf
+    lengths = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lengths[:7] = T
+    flat = torch.zeros(B * T * V + 8, dtype=torch.float32, device="cuda")
+    view = flat[offset: offset + B * T * V].view(B, T, V)
+    view.copy_(torch.from_numpy(x))
+    d_len = torch.from_numpy(lengths).cuda()
+    for fix in (0, 1):
+        ids = torch.full((B, T), -1, dtype=torch.int32, device="cuda")
+        tok = torch.zeros((B, T), dtype=torch.int32, device="cuda")
+        ln = torch.zeros(B, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.load().coral_ctc_greedy(view.data_ptr(), d_len.data_ptr(), B, T, V, V - 1, fix, ids.data_ptr(),
+                                                tok.data_ptr(), ln.data_ptr(), _lib.stream_ptr(view.device)))
+        got = ids.cpu().numpy()
+        ref = np.argmax(x, axis=-1)
+        if fix:
+            ref = ref.copy()
+            ref[np.all(x == -100.0, axis=-1)] = V - 1
+        for b in range(B):
+            assert np.array_equal(got[b, : lengths[b]], ref[b, : lengths[b]]), (b, fix)
+
+
 def test_compute_error_rate_metrics_matches_oracle(torch_cuda, rng):
     from types import SimpleNamespace
 
