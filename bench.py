@@ -419,6 +419,38 @@ def run_ours(args, rank, world, local_rank):
     # ---- work counters (one extra untimed launch with stats)
     st = dec.decode_padded(d_logits, d_len, beam_width=args.beam, n_best=1, collect_stats=True).stats
 
+    # ---- the other kernels of the path, timed alone on the same inputs (rank 0; not part of `value`)
+    other = None
+    if rank == 0:
+        from coral_b200.greedy import greedy_decode_device
+
+        def timed(fn, n=7):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts))
+
+        g_ms = timed(lambda: greedy_decode_device(d_logits, d_len, blank_id=45))
+        fr = int(wl.lengths.sum())
+        g_bytes = fr * 46 * 4 + 2 * fr * 4  # logits read once; ids written, re-read by the collapse
+        hyp_cps0 = cp_table[dec.decode_launch(d_logits, d_len, None, beam_width=args.beam, n_best=1)[3].view(B, Tm).to(torch.int64)]
+        d_l0 = dec.decode_launch(d_logits, d_len, None, beam_width=args.beam, n_best=1)[4].view(B).to(torch.int64)
+        ml = max(ref_max_len, int(d_l0.max().item()))
+        e_ms = timed(lambda: metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps0, d_hbeg, d_hbeg + d_l0, B, 1, ml))
+        cells = float((torch.from_numpy(np.diff(r_off)).to(dev).double() * d_l0.double()).sum().item())
+        other = {
+            "ctc_argmax_kernel+ctc_collapse_kernel": {
+                "ms": g_ms, "algorithmic_bytes": g_bytes, "GB_per_s": g_bytes / g_ms / 1e6, "bound": "hbm",
+                "note": "greedy decode of the same logits (configs[0] / config 4 path); inputs 425 MB > L2"},
+            "edit_counts_kernel(chars)": {
+                "ms": e_ms, "cells": cells, "GCUPS": cells / e_ms / 1e6, "bound": "integer ALU / shared memory"},
+        }
+
     if rank == 0:
         frames = int(wl.lengths.sum())
         audio = float(synth.audio_seconds(wl.lengths).sum())
@@ -442,6 +474,9 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        if other:
+            g = other["ctc_argmax_kernel+ctc_collapse_kernel"]
+            g["frac_of_hbm_peak"] = g["GB_per_s"] / peak
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "beam_kernel_traffic.json"))).get("dram_bytes_per_launch") if B == 8192 else None
@@ -473,6 +508,7 @@ def run_ours(args, rank, world, local_rank):
             "beam_extensions_per_s": float(st[0]) / (beam_ms * 1e-3),
             "device_counters_per_step": {"beam_extensions": int(st[0]), "lm_word_scorings": int(st[1]),
                                          "ngram_probes": int(st[2]), "frames": int(st[3]), "lexicon_probes": int(st[4])},
+            "other_kernels": other,
             "cpu_baseline": cpu_baseline,
             "parity_gate": parity,
             "quality": {"cer": cer_v, "wer": wer_v},

@@ -161,58 +161,60 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   uint32_t wf_cap = FRAMES ? (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu) : 0u;
   size_t off[7];
   const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
+  std::lock_guard<std::mutex> lock(dec->mu);
+  coral_decoder::Scratch& S = dec->scratch[(void*)st];
   size_t free_b = 0, total_b = 0;
   CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + dec->scratch_bytes) / 2);
+  const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + S.scratch_bytes) / 2);
   uint32_t n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(want, budget / slot_bytes));
-  const bool fits = dec->d_scratch && dec->node_cap >= node_cap && dec->bnd_cap >= bnd_cap &&
-                    dec->ch_size >= ch_size && dec->outs_cap >= outs_cap && dec->wf_cap >= wf_cap &&
-                    dec->n_slots >= n_slots;
+  const bool fits = S.d_scratch && S.node_cap >= node_cap && S.bnd_cap >= bnd_cap &&
+                    S.ch_size >= ch_size && S.outs_cap >= outs_cap && S.wf_cap >= wf_cap &&
+                    S.n_slots >= n_slots;
   if (fits) {
     // reuse the arena with the (larger) capacities it was laid out for
-    node_cap = dec->node_cap;
-    bnd_cap = dec->bnd_cap;
-    ch_size = dec->ch_size;
-    outs_cap = dec->outs_cap;
-    wf_cap = dec->wf_cap;
+    node_cap = S.node_cap;
+    bnd_cap = S.bnd_cap;
+    ch_size = S.ch_size;
+    outs_cap = S.outs_cap;
+    wf_cap = S.wf_cap;
   } else {
-    node_cap = std::max(node_cap, dec->node_cap);
-    bnd_cap = std::max(bnd_cap, dec->bnd_cap);
-    ch_size = std::max(ch_size, dec->ch_size);
-    outs_cap = std::max(outs_cap, dec->outs_cap);
-    wf_cap = std::max(wf_cap, dec->wf_cap);
+    node_cap = std::max(node_cap, S.node_cap);
+    bnd_cap = std::max(bnd_cap, S.bnd_cap);
+    ch_size = std::max(ch_size, S.ch_size);
+    outs_cap = std::max(outs_cap, S.outs_cap);
+    wf_cap = std::max(wf_cap, S.wf_cap);
     const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
-    n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max(want, dec->n_slots), budget / sb));
-    // wait for earlier launches that may still use the old arena, then rebuild it
-    CORAL_CUDA_OK(cudaDeviceSynchronize());
-    if (dec->d_scratch) cudaFree(dec->d_scratch);
-    dec->d_scratch = nullptr;
-    dec->scratch_bytes = 0;
-    dec->n_slots = 0;
+    n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max(want, S.n_slots), budget / sb));
+    // wait for this stream's earlier launches, which may still use the old arena, then rebuild it
+    CORAL_CUDA_OK(cudaStreamSynchronize(st));
+    if (S.d_scratch) cudaFree(S.d_scratch);
+    S.d_scratch = nullptr;
+    S.scratch_bytes = 0;
+    S.n_slots = 0;
     const size_t bytes = sb * n_slots;
-    CORAL_CUDA_OK(cudaMalloc(&dec->d_scratch, bytes));
+    CORAL_CUDA_OK(cudaMalloc(&S.d_scratch, bytes));
     // nothing to initialise: every arena is written before it is read (the kernel clears the
     // part of the child table an utterance uses)
-    dec->scratch_bytes = bytes;
-    dec->slot_bytes = sb;
-    dec->n_slots = n_slots;
-    dec->node_cap = node_cap;
-    dec->bnd_cap = bnd_cap;
-    dec->ch_size = ch_size;
-    dec->outs_cap = outs_cap;
-    dec->wf_cap = wf_cap;
+    S.scratch_bytes = bytes;
+    S.slot_bytes = sb;
+    S.n_slots = n_slots;
+    S.node_cap = node_cap;
+    S.bnd_cap = bnd_cap;
+    S.ch_size = ch_size;
+    S.outs_cap = outs_cap;
+    S.wf_cap = wf_cap;
   }
-  if (!dec->d_work) CORAL_CUDA_OK(cudaMalloc(&dec->d_work, sizeof(int32_t)));
-  CORAL_CUDA_OK(cudaMemsetAsync(dec->d_work, 0, sizeof(int32_t), st));
-  L.scratch = dec->d_scratch;
-  L.slot_bytes = dec->slot_bytes;
+  if (!S.d_work) CORAL_CUDA_OK(cudaMalloc(&S.d_work, sizeof(int32_t)));
+  CORAL_CUDA_OK(cudaMemsetAsync(S.d_work, 0, sizeof(int32_t), st));
+  L.scratch = S.d_scratch;
+  L.slot_bytes = S.slot_bytes;
   L.node_cap = node_cap;
   L.bnd_cap = bnd_cap;
   L.ch_size = ch_size;
   L.outs_cap = outs_cap;
   L.wf_cap = wf_cap;
-  L.work = dec->d_work;
-  const uint32_t grid = std::min<uint32_t>(dec->n_slots, std::max<uint32_t>(1, want));
+  L.work = S.d_work;
+  const uint32_t grid = std::min<uint32_t>(S.n_slots, std::max<uint32_t>(1, want));
   kern<<<grid, NT, smem, st>>>(L);
   CORAL_CUDA_OK(cudaGetLastError());
   return CORAL_OK;
@@ -285,8 +287,10 @@ int32_t coral_decoder_free(coral_decoder* d) {
   DeviceGuard g(d->device);
   cudaDeviceSynchronize();
   if (d->d_lex) cudaFree(d->d_lex);
-  if (d->d_scratch) cudaFree(d->d_scratch);
-  if (d->d_work) cudaFree(d->d_work);
+  for (auto& kv : d->scratch) {
+    if (kv.second.d_scratch) cudaFree(kv.second.d_scratch);
+    if (kv.second.d_work) cudaFree(kv.second.d_work);
+  }
   delete d;
   return CORAL_OK;
 }
@@ -304,7 +308,11 @@ int32_t coral_decoder_set_params(coral_decoder* d, double alpha, double beta, do
 int32_t coral_decoder_info(const coral_decoder* d, uint64_t* lexicon_entries, uint64_t* device_bytes) {
   if (!d) return fail(CORAL_EARG, "coral_decoder_info: null handle");
   if (lexicon_entries) *lexicon_entries = d->lex.n_entries;
-  if (device_bytes) *device_bytes = d->device_bytes + d->scratch_bytes;
+  if (device_bytes) {
+    uint64_t sb = 0;
+    for (const auto& kv : d->scratch) sb += kv.second.scratch_bytes;
+    *device_bytes = d->device_bytes + sb;
+  }
   return CORAL_OK;
 }
 

@@ -1,5 +1,7 @@
 // Opaque handle definitions shared by the C-ABI translation units.
 #pragma once
+#include <map>
+#include <mutex>
 #include <stdint.h>
 
 #include "beam_core.h"
@@ -21,12 +23,17 @@ struct coral_decoder {
   coral::LexSlot* d_lex = nullptr;
   coral::DecodeParams P;   // alphabet + current alpha/beta/unk/boundary
   int device = 0;
-  // scratch arenas in HBM, grown lazily, reused call after call
-  uint8_t* d_scratch = nullptr;
-  size_t scratch_bytes = 0;
-  size_t slot_bytes = 0;
-  uint32_t n_slots = 0;
-  uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0, wf_cap = 0;
-  int32_t* d_work = nullptr;
+  // scratch arenas in HBM, one set per CUDA stream the decoder is used on (launches on
+  // different streams may overlap), grown lazily, reused call after call
+  struct Scratch {
+    uint8_t* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    size_t slot_bytes = 0;
+    uint32_t n_slots = 0;
+    uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0, wf_cap = 0;
+    int32_t* d_work = nullptr;
+  };
+  std::map<void*, Scratch> scratch;
+  std::mutex mu;
   uint64_t device_bytes = 0;
 };

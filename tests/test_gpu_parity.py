@@ -409,6 +409,32 @@ def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, 
         beams_equal(oracle_decoder.decode_beams(x), g)
 
 
+def test_concurrent_streams_share_one_decoder(gpu_decoder, torch_cuda, cache_dir):
+    """Launches of the same decoder handle on different CUDA streams may overlap: each stream
+    has its own scratch arenas and work counter (SURVEY 8b threading contract)."""
+    from coral_b200 import synth
+
+    torch = torch_cuda
+    w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
+    d_logits = torch.from_numpy(w.logits).cuda()
+    d_len = torch.from_numpy(w.lengths).cuda()
+    want = gpu_decoder.decode_padded(d_logits, d_len, n_best=2)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        for k, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                a0, b0 = 64 * k, 64 * (k + 1)
+                outs.append((a0, b0, gpu_decoder.decode_launch(d_logits[a0:b0], d_len[a0:b0], None, n_best=2)))
+    torch.cuda.synchronize()
+    for a0, b0, (d_n, d_logit, d_comb, d_tok, d_lens, d_status) in outs:
+        assert int(d_status.sum().item()) == 0
+        assert np.array_equal(d_n.cpu().numpy(), want.n_beams[a0:b0])
+        assert np.array_equal(d_tok.cpu().numpy(), want.tokens[a0:b0])
+        assert np.array_equal(d_comb.cpu().numpy()[:, 0], want.lm_score[a0:b0, 0])
+
+
 # ------------------------------------------------------------------- golden fixtures on GPU
 def _golden(name):
     import json

@@ -61,3 +61,51 @@ if which in ("all", "config3"):
         for tmin in (-3.0, -5.0, -7.0, -10.0, -20.0):
             run_cell(dec, odec, wl, d_logits, d_len, 200, tmin, n_check=1,
                      tag=dict(config=3, lm_order=5, logits=kind, T_max=int(wl.lengths.max())))
+
+if which in ("all", "config3flat"):
+    wl = synth.build_workload(cache, 256, order=5, kind="flat", shape="conversation", name="convflat")
+    dec = build_ctcdecoder(wl.labels, wl.arpa_path)
+    odec = oracle_build(wl.labels, wl.arpa_path)
+    d_logits = torch.from_numpy(wl.logits).to(dev)
+    d_len = torch.from_numpy(wl.lengths).to(dev)
+    for tmin in (-3.0, -5.0):
+        run_cell(dec, odec, wl, d_logits, d_len, 200, tmin, n_check=1,
+                 tag=dict(config=3, lm_order=5, logits="flat", T_max=int(wl.lengths.max())))
+
+if which in ("all", "config2"):
+    # the headline workload presented as one batch, in the reference's batches of 16
+    # (R:config/evaluation.yaml:20), and its flat-logit stress variant
+    for kind in ("peaky", "flat"):
+        n = 8192 if kind == "peaky" else 1776
+        wl = synth.build_workload(cache, n, order=5, kind=kind, name="eval0")
+        dec = build_ctcdecoder(wl.labels, wl.arpa_path)
+        odec = oracle_build(wl.labels, wl.arpa_path)
+        d_logits = torch.from_numpy(wl.logits).to(dev)
+        d_len = torch.from_numpy(wl.lengths).to(dev)
+        run_cell(dec, odec, wl, d_logits, d_len, 100, -5.0, n_check=2,
+                 tag=dict(config=2, lm_order=5, logits=kind, presentation="one batch"))
+        if kind == "peaky":
+            nb = 1024
+            for _ in range(2):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for a0 in range(0, nb, 16):
+                    dec.decode_launch(d_logits[a0:a0 + 16], d_len[a0:a0 + 16], None, beam_width=100)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+            print(json.dumps(dict(config=2, lm_order=5, logits=kind, presentation="batches of 16, one stream, back to back",
+                                  beam=100, utts=nb, ms=round(ms, 2), utt_per_s=round(nb / ms * 1e3))), flush=True)
+            streams = [torch.cuda.Stream() for _ in range(16)]
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for k, a0 in enumerate(range(0, nb, 16)):
+                    with torch.cuda.stream(streams[k % len(streams)]):
+                        dec.decode_launch(d_logits[a0:a0 + 16], d_len[a0:a0 + 16], None, beam_width=100)
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) * 1e3
+            print(json.dumps(dict(config=2, lm_order=5, logits=kind, presentation="batches of 16 round-robin over 16 streams (wall clock)",
+                                  beam=100, utts=nb, ms=round(ms, 2), utt_per_s=round(nb / ms * 1e3))), flush=True)
+        del dec, d_logits
