@@ -730,12 +730,10 @@ struct BeamDecoder {
 
   static CORAL_DEV void expand_item(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
                                     const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs,
-                                    double bscale, int K, uint32_t nN, uint32_t n1, uint32_t i,
+                                    double bscale, int K, bool fam2, uint32_t j, uint32_t k_in,
                                     unsigned long long& lmax) {
     {
       {
-        const bool fam2 = i >= n1;
-        const uint32_t j = fam2 ? i - n1 : i / K;
         const int s = sm.ne_slot[j];
         const uint32_t rb = rep_beam(sm, s);
         const uint32_t mt = sm.meta[cur][rb];
@@ -760,7 +758,7 @@ struct BeamDecoder {
                (uint32_t)k * nb + first, 0u, 0u, rb, c, 0u, lmax, mem[nm - 1]);
           return;
         }
-        const uint32_t k = i % K;
+        const uint32_t k = k_in;
         const uint32_t c = sm.kept[f][k];
         const double p = (double)sm.lp[f][c];
         if ((int)c == P.blank_id) {
@@ -852,10 +850,19 @@ struct BeamDecoder {
         sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
         if (io.stats) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
       }
+      // Work units = (token group g, chunk of 32 nodes); group K is the "repeat" family. A warp
+      // takes whole units, so its lanes follow the same code path (same token kind) instead of
+      // serialising the blank / space / letter / repeat paths inside every warp, and the groups
+      // of a typical frame (K + 1 <= 4) run side by side on the CTA's warps.
       unsigned long long lmax = 0;
-      const uint32_t n1 = nN * (uint32_t)K;
-      for (uint32_t i = lane; i < n1 + nN; i += NT) {
-        expand_item(sm, lm, P, sc, io, f, cur, q, nb, outs, bscale, K, nN, n1, i, lmax);
+      const uint32_t nchunks = (nN + 31u) >> 5;
+      const uint32_t units = ((uint32_t)K + 1u) * nchunks;
+      constexpr uint32_t kWarps = NT / 32;
+#pragma unroll 1
+      for (uint32_t u = (uint32_t)lane >> 5; u < units; u += kWarps) {
+        const uint32_t g = u / nchunks;
+        const uint32_t j = (u - g * nchunks) * 32u + ((uint32_t)lane & 31u);
+        if (j < nN) expand_item(sm, lm, P, sc, io, f, cur, q, nb, outs, bscale, K, g == (uint32_t)K, j, g, lmax);
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
@@ -1149,8 +1156,19 @@ struct BeamDecoder {
     pt.start(io.stats);
     hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]], &lm, &P, &sc, f);
     pt.mark(8);
+#if defined(__CUDA_ARCH__)
+    const uint32_t bnd_before = sm.bnd_count;
+    const long long t_exp = io.stats ? clock64() : 0;
+#endif
     expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
     pt.mark(9);
+#if defined(__CUDA_ARCH__)
+    if (io.stats && threadIdx.x == 0) {  // tuning: expand time split by "frame scored a word with the LM"
+      const int slot = sm.bnd_count != bnd_before ? 5 : 6;
+      sm.opc[slot] += (unsigned long long)(clock64() - t_exp);
+      sm.opn[slot] += 1u;
+    }
+#endif
     if (sm.status != 0) return;  // uniform: written before the barrier that ends expand
     const unsigned long long thr = prune_key(sm, P, q);
     if (sm.n_out[q] > (uint32_t)OUTC) {
