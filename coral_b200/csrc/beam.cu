@@ -144,10 +144,17 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
   const size_t smem = sizeof(typename Dec::Sm);
   auto kern = beam_search_kernel<NT, BW, OUTC, FRAMES>;
-  CORAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-  if (per_sm < 1) return fail(CORAL_ECUDA, "beam kernel does not fit on an SM");
+  // occupancy of this instantiation, queried once per device (the runtime calls are not free
+  // and this function sits on the latency path of small batches)
+  static int per_sm_cache[64] = {0};
+  const int dev_slot = dec->device & 63;
+  int per_sm = per_sm_cache[dev_slot];
+  if (per_sm == 0) {
+    CORAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) return fail(CORAL_ECUDA, "beam kernel does not fit on an SM");
+    per_sm_cache[dev_slot] = per_sm;
+  }
   const uint32_t want = (uint32_t)std::min<int64_t>((int64_t)B, (int64_t)per_sm * sm_count(dec->device));
 
   // scratch: worst-case arenas per slot (every frame can add beam_width back-pointer records
@@ -163,13 +170,13 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
   std::lock_guard<std::mutex> lock(dec->mu);
   coral_decoder::Scratch& S = dec->scratch[(void*)st];
-  size_t free_b = 0, total_b = 0;
-  CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + S.scratch_bytes) / 2);
-  uint32_t n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(want, budget / slot_bytes));
+  // the arena is reused as long as its per-slot capacities cover this launch and it has a slot
+  // for every CTA the launch wants (or was already capped by the memory budget); only a
+  // (re)allocation queries the free memory
+  uint32_t n_slots = want;
   const bool fits = S.d_scratch && S.node_cap >= node_cap && S.bnd_cap >= bnd_cap &&
                     S.ch_size >= ch_size && S.outs_cap >= outs_cap && S.wf_cap >= wf_cap &&
-                    S.n_slots >= n_slots;
+                    (S.n_slots >= want || S.budget_capped);
   if (fits) {
     // reuse the arena with the (larger) capacities it was laid out for
     node_cap = S.node_cap;
@@ -184,7 +191,12 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
     outs_cap = std::max(outs_cap, S.outs_cap);
     wf_cap = std::max(wf_cap, S.wf_cap);
     const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
-    n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max(want, S.n_slots), budget / sb));
+    size_t free_b = 0, total_b = 0;
+    CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + S.scratch_bytes) / 2);
+    const size_t wanted = std::max(want, S.n_slots);
+    n_slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(wanted, budget / sb));
+    S.budget_capped = n_slots < wanted;
     // wait for this stream's earlier launches, which may still use the old arena, then rebuild it
     CORAL_CUDA_OK(cudaStreamSynchronize(st));
     if (S.d_scratch) cudaFree(S.d_scratch);

@@ -191,7 +191,10 @@ struct UttIO {
   unsigned long long* stats;
 };
 
-constexpr int kNB = 64;             // score buckets over the prune window
+#ifndef CORAL_KNB
+#define CORAL_KNB 128
+#endif
+constexpr int kNB = CORAL_KNB;      // score buckets over the prune window (<= 256, multiple of 8)
 
 // per-beam word timing (pyctcdecode's part_frames and text_frames), present only in the
 // word-frame instantiation of the kernel

@@ -230,10 +230,18 @@ int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, in
   if (T_max > 0) {
     const size_t smem = (((size_t)kTileFrames * V * sizeof(float) + 15) & ~(size_t)15) + 32;
     if (smem > 200 * 1024) return fail(CORAL_EARG, "vocabulary too large for the greedy kernel's tiles");
-    CORAL_CUDA_OK(cudaFuncSetAttribute(ctc_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, per_sm = 0;
+    int dev = 0;
     CORAL_CUDA_OK(cudaGetDevice(&dev));
-    CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_argmax_kernel, kTileFrames, smem));
+    // occupancy for this tile size, queried once per (device, shared-memory size)
+    static int cache_per_sm[64] = {0};
+    static size_t cache_smem[64] = {0};
+    int per_sm = (cache_smem[dev & 63] == smem) ? cache_per_sm[dev & 63] : 0;
+    if (per_sm == 0) {
+      CORAL_CUDA_OK(cudaFuncSetAttribute(ctc_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_argmax_kernel, kTileFrames, smem));
+      cache_per_sm[dev & 63] = per_sm;
+      cache_smem[dev & 63] = smem;
+    }
     const long long n_tiles = (long long)B * ((T_max + kTileFrames - 1) / kTileFrames);
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(n_tiles, (long long)std::max(per_sm, 1) * sm_count(dev)));
     ctc_argmax_kernel<<<grid, kTileFrames, smem, st>>>(logits_dev, lengths_dev, B, T_max, V, blank_id, pad_fixup, ids);
