@@ -163,7 +163,7 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   const uint64_t bw = (uint64_t)L.P.beam_width;
   uint32_t node_cap = (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu);
   uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
-  uint32_t ch_size = 9 * (uint32_t)T + 16;  // floats of row-sum scratch: [T] sums + [T][8] partials
+  uint32_t ch_size = (uint32_t)T + 16;  // floats of row-sum scratch (input classification)
   uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
   uint32_t wf_cap = FRAMES ? (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu) : 0u;
   size_t off[7];

@@ -470,7 +470,10 @@ struct BeamDecoder {
   // x_max, tmp = x - x_max, exp, sum (numpy pairwise order for a
   // contiguous row of n <= 128: eight strided accumulators, combined as a balanced tree,
   // remainder added in order), log, tmp - log, clip to [log(1e-15), 0].
-  static CORAL_DEV_OUTLINE void stage_frames(Sm& sm, const DecodeParams& P, const UttIO& io, int t0, int nf) {
+  // `rowsum` != nullptr: also record each raw row's float32 sum in numpy's order (the input
+  // test of classify_rowsums), from the values already staged in shared memory.
+  static CORAL_DEV_OUTLINE void stage_frames(Sm& sm, const DecodeParams& P, const UttIO& io, int t0, int nf,
+                                             float* rowsum) {
     const int V = P.V;
     CORAL_LANES(NT) {
 #pragma unroll 2
@@ -489,6 +492,8 @@ struct BeamDecoder {
     CORAL_GSYNC(NT);
     const float lo = -34.538776f;  // float32(log(1e-15))
     const bool as_prob = P.input_mode == 2 || (P.input_mode == 0 && sm.is_prob);
+    float* rs8 = reinterpret_cast<float*>(sm.o_order);   // [kChunk][8] strided partial row sums
+    float* rem8 = reinterpret_cast<float*>(sm.o_aux);    // [kChunk][8] raw tail elements (V % 8)
     if (as_prob) {
       CORAL_LANES(NT) {
         for (int i = lane; i < nf * V; i += NT) {
@@ -502,6 +507,11 @@ struct BeamDecoder {
       CORAL_LANES(NT) {
         for (int f = lane; f < nf; f += NT) {
           float* row = sm.lp[f];
+          if (rowsum) {
+            float r = 0.0f;
+            for (int v = 0; v < V; ++v) r = f32_add(r, row[v]);
+            rowsum[t0 + f] = r;
+          }
           float mx = row[0];
           for (int v = 1; v < V; ++v) mx = row[v] > mx ? row[v] : mx;
           if (!isfinite(mx)) mx = 0.0f;
@@ -529,6 +539,13 @@ struct BeamDecoder {
 #pragma unroll 1
           for (int i = j + 8; i < V; i += 8) m = row[i] > m ? row[i] : m;
           pmax[p] = m;
+          if (rowsum) {
+            float r = row[j];
+#pragma unroll 1
+            for (int i = j + 8; i < main_n; i += 8) r = f32_add(r, row[i]);
+            rs8[p] = r;
+            rem8[p] = main_n + j < V ? row[main_n + j] : 0.0f;
+          }
         }
       }
       CORAL_GSYNC(NT);
@@ -536,6 +553,14 @@ struct BeamDecoder {
         for (int p = lane; p < nf * 8; p += NT) {
           const int f = p >> 3, j = p & 7;
           float* row = sm.lp[f];
+          if (rowsum && j == 0) {
+            const float* r = rs8 + f * 8;
+            float rs = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])),
+                               f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
+#pragma unroll 1
+            for (int i = main_n; i < V; ++i) rs = f32_add(rs, rem8[f * 8 + (i - main_n)]);
+            rowsum[t0 + f] = rs;
+          }
           float mx = pmax[f * 8];
 #pragma unroll 1
           for (int k = 1; k < 8; ++k) mx = pmax[f * 8 + k] > mx ? pmax[f * 8 + k] : mx;
@@ -1275,44 +1300,20 @@ struct BeamDecoder {
   }
 
   // ---- pyctcdecode's probabilities-vs-logits test for one utterance -> sm.is_prob.
-  // Row sums replay numpy's float32 order (eight strided accumulators = eight lanes per row,
-  // coalesced reads; balanced combine; remainder in order). The mean of the row sums is first
-  // bounded with a double-precision total: unless it lies within 1e-3 of 1 the float32 mean
-  // cannot be exactly 1.0f whatever the summation order (float32 pairwise error is < 1e-5
-  // relative), and only then one lane replays numpy's pairwise order over the T row sums.
-  static CORAL_DEV_OUTLINE void classify_input(Sm& sm, const DecodeParams& P, const SlotScratch& sc, const UttIO& io) {
+  // math.isclose(logits.sum(axis=1).mean(), 1) holds only when the float32 mean is exactly
+  // 1.0f. The row sums were recorded in numpy's order while the frames were staged (no second
+  // pass over the logits). Their mean is first bounded with a double-precision total: unless
+  // it lies within 1e-3 of 1 the float32 mean cannot be 1.0f whatever the summation order
+  // (float32 pairwise error is < 1e-5 relative), and only then one lane replays numpy's
+  // pairwise order over the T row sums.
+  static CORAL_DEV_OUTLINE void classify_rowsums(Sm& sm, const SlotScratch& sc, int T) {
     static_assert(OUTC >= NT, "the candidate arrays double as per-lane scratch");
-    const int V = P.V, T = io.T;
-    float* part = sc.rowsum + T;  // [T][8] strided partial sums
-    const int main_n = V - (V % 8);
-    if (V >= 8 && V <= 128) {
-      CORAL_LANES(NT) {
-        for (int p = lane; p < T * 8; p += NT) {
-          const int f = p >> 3, j = p & 7;
-          const float* row = io.logits + (size_t)f * V;
-          float r = row[j];
-#pragma unroll 4
-          for (int i = j + 8; i < main_n; i += 8) r = f32_add(r, row[i]);
-          part[p] = r;
-        }
-      }
-      CORAL_GSYNC(NT);
-    }
     double* dsum = reinterpret_cast<double*>(sm.o_logit);  // [NT], candidate arrays are idle here
     double* dabs = reinterpret_cast<double*>(sm.o_key);    // [NT]
     CORAL_LANES(NT) {
       double ds = 0.0, da = 0.0;
       for (int f = lane; f < T; f += NT) {
-        const float* row = io.logits + (size_t)f * V;
-        float s;
-        if (V >= 8 && V <= 128) {
-          const float* r = part + f * 8;
-          s = f32_add(f32_add(f32_add(r[0], r[1]), f32_add(r[2], r[3])), f32_add(f32_add(r[4], r[5]), f32_add(r[6], r[7])));
-          for (int i = main_n; i < V; ++i) s = f32_add(s, row[i]);
-        } else {
-          s = np_pairwise_sum(row, V);
-        }
-        sc.rowsum[f] = s;
+        const float s = sc.rowsum[f];
         ds += (double)s;
         da += (double)(s < 0.0f ? -s : s);
       }
@@ -1344,9 +1345,18 @@ struct BeamDecoder {
   }
 
   // ---- whole utterance ---------------------------------------------------------------------------
+  // With input_mode 0 (pyctcdecode's auto-detection) the utterance is decoded as logits while
+  // the row sums are recorded; in the rare case that they then say "probabilities", it is
+  // decoded again as such. Real callers pass logits, so nothing is read or done twice.
   static CORAL_DEV void decode(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc, const UttIO& io) {
+    int cur = 0, q = 0;
+    uint32_t nb = 1;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool speculate = P.input_mode == 0 && attempt == 0;
     CORAL_LANES(NT) {
       clear_hash(sm, lane);
+      if (lane == 0 && attempt == 0) sm.is_prob = 0;
       if (lane == 0) {
         sm.status = 0;
         for (int k = 0; k < 8; ++k) { sm.cnt[k] = 0; sm.opc[k] = 0; sm.opn[k] = 0; }
@@ -1379,19 +1389,14 @@ struct BeamDecoder {
       }
     }
     CORAL_GSYNC(NT);
-    // pyctcdecode's input test: math.isclose(logits.sum(axis=1).mean(), 1),
-    // which a float32 mean passes only when it is exactly 1.0f -- so both reductions replay
-    // numpy's summation order. Done per utterance here (no batch-wide pre-pass).
-    if (P.input_mode == 0) classify_input(sm, P, sc, io);
-    int cur = 0, q = 0;
-    uint32_t nb = 1;
+    cur = 0; q = 0; nb = 1;
     bool failed = false;
     for (int t0 = 0; t0 < io.T && !failed; t0 += kChunk) {
       const int nf = io.T - t0 < kChunk ? io.T - t0 : kChunk;
       {
         PhaseTimer ps;
         ps.start(io.stats);
-        stage_frames(sm, P, io, t0, nf);
+        stage_frames(sm, P, io, t0, nf, speculate ? sc.rowsum : nullptr);
         ps.mark(15);
       }
       for (int f = 0; f < nf; ++f) {
@@ -1407,6 +1412,10 @@ struct BeamDecoder {
       CORAL_GSYNC(NT);
       return;
     }
+    if (!speculate) break;
+    classify_rowsums(sm, sc, io.T);
+    if (!sm.is_prob) break;
+    }  // attempt
     finalize(sm, lm, P, sc, io, cur, q, nb);
   }
 };
