@@ -284,8 +284,6 @@ class BeamSearchDecoderCTC:
         the alphabet lookup and the compaction run on the GPU, one flat code-point buffer comes
         back, and the host only decodes UTF-32 and slices."""
         torch = _torch()
-        if not self._single_cp:
-            return self.tokens_to_text(d_tok.cpu().numpy(), d_lens.cpu().numpy())
         B, T = d_tok.shape
         dev = d_tok.device
         if getattr(self, "_d_cp_table", None) is None or self._d_cp_table.device != dev:
@@ -293,6 +291,10 @@ class BeamSearchDecoderCTC:
         lens = d_lens.to(torch.int64)
         mask = torch.arange(T, device=dev)[None, :] < lens[:, None]
         flat = self._d_cp_table[d_tok[mask].to(torch.int64)]
+        # labels longer than one code point (CoRal's "<s>" / "</s>") have no table entry; they
+        # practically never win, so one scalar tells whether the host path is needed at all
+        if not self._single_cp and bool((flat == 0).any().item()):
+            return self.tokens_to_text(d_tok.cpu().numpy(), d_lens.cpu().numpy())
         off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
         torch.cumsum(lens, 0, out=off[1:])
         text = flat.cpu().numpy().view(np.uint32).tobytes().decode("utf-32-le")

@@ -306,6 +306,15 @@ def test_beam_search_no_lm_edge_cases_and_errors(torch_cuda, small_workload, rng
     import math
     if math.isclose(float(p.sum(axis=1).mean()), 1):
         beams_equal(o.decode_beams(p), g.decode_beams_batch(None, [p])[0])
+    # a multi-code-point label ("<s>", id 42) that wins: decode_batch must fall back from the
+    # device-side text path and still spell it out
+    sp = np.full((12, 46), -8.0, np.float32)
+    sp[:, 45] = 0.0
+    sp[2, 42] = 6.0
+    sp[5, 17] = 6.0
+    sp[8, 43] = 6.0
+    assert g.decode_batch(None, [sp, lg[0]]) == [o.decode(sp), o.decode(lg[0])]
+    assert "<s>" in o.decode(sp)
     with pytest.raises(ValueError):
         g.decode_beams(np.zeros((10, 40), np.float32))
     with pytest.raises(ValueError):
