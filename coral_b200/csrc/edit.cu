@@ -97,34 +97,38 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
                    const int64_t* __restrict__ hyp_beg, const int64_t* __restrict__ hyp_end, int64_t n_pairs,
                    int mode, int32_t* __restrict__ out_sdih, int32_t* __restrict__ out_status, uint8_t* gwork,
                    size_t gwork_stride, int gcap) {
-  constexpr int SCAP = GLOBAL_WORK ? 32 : LCAP;
+  // Every warp owns a shared-memory work area for strings of up to LCAP symbols; with
+  // GLOBAL_WORK it also owns a larger one in HBM and picks per pair: only the pairs that do
+  // not fit on chip pay for the off-chip matrix.
+  constexpr int SCAP = LCAP;
   __shared__ uint32_t s_tok[WARPS][2][SCAP];
   __shared__ int32_t s_edge[WARPS][SCAP + 1];
   __shared__ uint32_t s_bits[WARPS][2][SCAP * (SCAP / 32)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
-  EditWork W;
+  EditWork Wg, Ws;
   if (GLOBAL_WORK) {
     uint8_t* b = gwork + (size_t)gw * gwork_stride;
-    W.cap = gcap;
-    W.tok1 = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * 4;
-    W.tok2 = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * 4;
-    W.edge = reinterpret_cast<int32_t*>(b); b += ((size_t)gcap + 32) * 4;
-    W.vp = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * (gcap / 32) * 4;
-    W.vn = reinterpret_cast<uint32_t*>(b);
-  } else {
-    W.cap = LCAP;
-    W.tok1 = s_tok[warp][0];
-    W.tok2 = s_tok[warp][1];
-    W.edge = s_edge[warp];
-    W.vp = s_bits[warp][0];
-    W.vn = s_bits[warp][1];
+    Wg.cap = gcap;
+    Wg.tok1 = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * 4;
+    Wg.tok2 = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * 4;
+    Wg.edge = reinterpret_cast<int32_t*>(b); b += ((size_t)gcap + 32) * 4;
+    Wg.vp = reinterpret_cast<uint32_t*>(b); b += (size_t)gcap * (gcap / 32) * 4;
+    Wg.vn = reinterpret_cast<uint32_t*>(b);
   }
+  Ws.cap = LCAP;
+  Ws.tok1 = s_tok[warp][0];
+  Ws.tok2 = s_tok[warp][1];
+  Ws.edge = s_edge[warp];
+  Ws.vp = s_bits[warp][0];
+  Ws.vn = s_bits[warp][1];
   for (int64_t pair = gw; pair < n_pairs; pair += nwarps) {
     __syncwarp();
     const int64_t r0 = ref_beg[pair], r1 = ref_end[pair];
     const int64_t h0 = hyp_beg[pair], h1 = hyp_end[pair];
+    const bool on_chip = !GLOBAL_WORK || (r1 - r0 <= LCAP && h1 - h0 <= LCAP);
+    const EditWork W = on_chip ? Ws : Wg;
     int n1 = 0, n2 = 0;
     int status = (r1 == r0) ? 1 : 0;
     if (mode == CORAL_EDIT_TOKENS) {
@@ -306,7 +310,7 @@ int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_
     const int cap = (int)std::max<int64_t>(64, (max_len + 31) / 32 * 32);
     const size_t stride = ((size_t)cap * 4 * 2 + ((size_t)cap + 32) * 4 + (size_t)cap * (cap / 32) * 4 * 2 + 15) & ~(size_t)15;
     const int64_t need = (n_pairs + WARPS - 1) / WARPS;
-    const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * 4);
     const size_t bytes = stride * WARPS * grid;
     if (g_edit_work_bytes[device] < bytes) {
       CORAL_CUDA_OK(cudaDeviceSynchronize());
@@ -316,7 +320,7 @@ int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_
       CORAL_CUDA_OK(cudaMalloc(&g_edit_work[device], bytes));
       g_edit_work_bytes[device] = bytes;
     }
-    edit_counts_kernel<true, 32, WARPS><<<grid, WARPS * 32, 0, st>>>(
+    edit_counts_kernel<true, 128, WARPS><<<grid, WARPS * 32, 0, st>>>(
         ref_cps_dev, ref_begin_dev, ref_end_dev, hyp_cps_dev, hyp_begin_dev, hyp_end_dev, n_pairs, mode,
         out_sdih_dev, out_status_dev, g_edit_work[device], stride, cap);
   }
