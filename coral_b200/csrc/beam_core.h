@@ -762,6 +762,11 @@ struct BeamDecoder {
                                     unsigned long long& lmax) {
     {
       {
+#if defined(__CUDA_ARCH__)
+        const bool tim = io.stats != nullptr;  // tuning: where a letter item spends its cycles
+        const long long tA = tim ? clock64() : 0;
+        long long tB = 0, tC = 0, tD = 0;
+#endif
         const int s = sm.ne_slot[j];
         const uint32_t rb = rep_beam(sm, s);
         const uint32_t mt = sm.meta[cur][rb];
@@ -806,8 +811,14 @@ struct BeamDecoder {
           if ((int)c == P.space_id && sm.sb0[cs] != kNone16) mem[nm++] = sm.sb0[cs];
         }
         if (nm == 0) return;
+#if defined(__CUDA_ARCH__)
+        if (tim) tB = clock64();
+#endif
         const uint32_t first = merge_members(sm, cur, mem, nm, p, logit);
         const uint32_t order = k * nb + first;
+#if defined(__CUDA_ARCH__)
+        if (tim) tC = clock64();
+#endif
         if (cs >= 0) {
           const uint32_t crb = rep_beam(sm, cs);
           emit(sm, outs, sc.outs_cap, q, bscale,
@@ -858,8 +869,20 @@ struct BeamDecoder {
             }
             ps = partial_score(P, wlen_m + P.label_ncp[c], nfl);
           }
+#if defined(__CUDA_ARCH__)
+          if (tim) tD = clock64();
+#endif
           emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
                2u | (nfl << 2), lmax, mem[nm - 1]);
+#if defined(__CUDA_ARCH__)
+          if (tim) {
+            const long long tE = clock64();
+            atomicAdd(&sm.opc[0], (unsigned long long)(tB - tA)); atomicAdd(&sm.opn[0], 1u);
+            atomicAdd(&sm.opc[2], (unsigned long long)(tC - tB));
+            atomicAdd(&sm.opc[4], (unsigned long long)(tD - tC));
+            atomicAdd(&sm.opc[7], (unsigned long long)(tE - tD));
+          }
+#endif
         }
       }
     }

@@ -43,6 +43,8 @@ if os.environ.get("CORAL_PHASES"):
     ops = ["-", "lm_word_score", "-", "lex_find", "-"]
     print("op latency (cycles/call, calls/frame): " + ", ".join(
         f"{n}={st[16+i]/max(st[24+i],1):.0f}x{st[24+i]/fr:.2f}" for i, n in enumerate(ops)))
+    n0 = max(st[24], 1)
+    print(f"letter item (cycles): lookup+child-hash {st[16]/n0:.0f}, merge {st[18]/n0:.0f}, lexicon+penalty {st[20]/n0:.0f}, emit {st[23]/n0:.0f}  x{st[24]/fr:.1f}/frame")
     print(f"expand cycles: frames with LM scoring {st[21]/max(st[29],1):.0f} x{st[29]/fr:.2f} of frames, without {st[22]/max(st[30],1):.0f} x{st[30]/fr:.2f}")
     print(f"per frame: ext={st[0]/fr:.1f} lm_scorings={st[1]/fr:.2f} ngram_probes={st[2]/fr:.2f} lex_probes={st[4]/fr:.2f} nodes={st[5]/fr:.2f} radix_select_frames/utt={st[7]/a.utts:.2f}")
 if os.environ.get("CORAL_FRAMES"):
