@@ -444,6 +444,48 @@ def test_concurrent_streams_share_one_decoder(gpu_decoder, torch_cuda, cache_dir
         assert np.array_equal(d_comb.cpu().numpy()[:, 0], want.lm_score[a0:b0, 0])
 
 
+def test_pipeline_on_device_handoff(gpu_decoder, oracle_decoder, torch_cuda, tmp_path, rng):
+    """the ASR pipeline with ``pipeline_class=BatchedCTCWithLMPipeline`` decodes each
+    model batch on the GPU where the logits are produced. Same texts and word timestamps as the
+    stock pipeline driving the oracle decoder one utterance at a time (R:src/coral/evaluate.py:56-60)."""
+    import json
+
+    import coral_b200
+
+    coral_b200.install_shims()
+    from transformers import (AutomaticSpeechRecognitionPipeline, Wav2Vec2Config, Wav2Vec2CTCTokenizer,
+                              Wav2Vec2FeatureExtractor, Wav2Vec2ForCTC, pipeline)
+
+    from coral_b200 import synth
+    from coral_b200.pipeline import BatchedCTCWithLMPipeline
+
+    torch = torch_cuda
+    vocab = {c: i for i, c in enumerate(synth.CORAL_LABELS[:42])}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    tok = Wav2Vec2CTCTokenizer(str(tmp_path / "vocab.json"), unk_token="<unk>", pad_token="<pad>",
+                               bos_token="<s>", eos_token="</s>", word_delimiter_token="|")
+    fe = Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True)
+    torch.manual_seed(7)
+    cfg = Wav2Vec2Config(vocab_size=46, hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
+                         intermediate_size=64, conv_dim=(16,) * 7, pad_token_id=45, num_conv_pos_embeddings=16,
+                         num_conv_pos_embedding_groups=4)
+    model = Wav2Vec2ForCTC(cfg).eval()
+    with torch.no_grad():
+        model.lm_head.weight.mul_(40.0)  # random-init heads are flat; make a few tokens stand out
+    audios = [rng.standard_normal(int(16000 * d)).astype(np.float32) for d in (0.9, 1.4, 0.6, 1.1, 0.8)]
+    ours = pipeline("automatic-speech-recognition", model=model, tokenizer=tok, feature_extractor=fe,
+                    decoder=gpu_decoder, device=0, pipeline_class=BatchedCTCWithLMPipeline)
+    stock = pipeline("automatic-speech-recognition", model=model, tokenizer=tok, feature_extractor=fe,
+                     decoder=oracle_decoder, device=0)
+    assert type(stock) is AutomaticSpeechRecognitionPipeline
+    got = ours([a.copy() for a in audios], batch_size=4, return_timestamps="word")
+    ref = stock([a.copy() for a in audios], batch_size=4, return_timestamps="word")
+    assert [g["text"] for g in got] == [r["text"] for r in ref]
+    assert [g["chunks"] for g in got] == [r["chunks"] for r in ref]
+    one = ours(audios[1].copy(), decoder_kwargs={"beam_width": 20})
+    assert one["text"] == stock(audios[1].copy(), decoder_kwargs={"beam_width": 20})["text"]
+
+
 # ------------------------------------------------------------------- golden fixtures on GPU
 def _golden(name):
     import json
