@@ -358,6 +358,18 @@ def test_hf_processor_with_lm_drop_in(gpu_decoder, oracle_decoder, small_workloa
     for offs, r in zip(wo.word_offsets, ref):
         assert [(d["word"], (d["start_offset"], d["end_offset"])) for d in offs] == \
                [(wd, (int(a), int(b))) for wd, (a, b) in r[2]]
+    # n_best > 1 and the LM weights HF forwards to reset_params (HF:...processing_wav2vec2_with_lm.py:365-367)
+    nb = proc.batch_decode(w.logits[:4], n_best=3, alpha=0.8, beta=0.7, unk_score_offset=-6.0, lm_score_boundary=False)
+    try:
+        oracle_decoder.reset_params(alpha=0.8, beta=0.7, unk_score_offset=-6.0, lm_score_boundary=False)
+        for u in range(4):
+            rb = oracle_decoder.decode_beams(w.logits[u, : w.lengths[u]])[:3]
+            assert list(nb.text[u]) == [b[0] for b in rb]
+            for a, b in zip(nb.lm_score[u], rb):
+                assert abs(a - b[4]) <= 1e-4 * max(1.0, abs(b[4]))
+    finally:
+        oracle_decoder.reset_params(alpha=0.5, beta=1.5, unk_score_offset=-10.0, lm_score_boundary=True)
+        gpu_decoder.reset_params(alpha=0.5, beta=1.5, unk_score_offset=-10.0, lm_score_boundary=True)
     # round trip through pyctcdecode's directory layout
     proc.save_pretrained(str(tmp_path / "m"))
     assert (tmp_path / "m" / "alphabet.json").exists() and (tmp_path / "m" / "language_model" / "attrs.json").exists()
