@@ -2,7 +2,7 @@
 sweep. Kernel-only utt/s (CUDA events, min of 3) plus a transcript parity check against the oracle
 on a couple of utterances per cell. Prints one JSON line per cell."""
 import json, os, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it uses the oracle as checker)
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from coral_b200 import synth
