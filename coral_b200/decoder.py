@@ -37,7 +37,7 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 MAX_BEAM_WIDTH = 512
-H2D_CHUNK = 512  # utterances per host->device chunk when the logits arrive from pinned host memory
+H2D_CHUNK = int(os.environ.get("CORAL_H2D_CHUNK", "512"))  # utterances per host->device chunk (pinned host logits)
 # (large chunks: a launch with few utterances per CTA is dominated by its longest utterances)
 
 
