@@ -21,6 +21,8 @@ SIGNATURES = {
     "coral_last_error": (C.c_char_p, []),
     "coral_abi_version": (_i32, []),
     "coral_lm_load_arpa": (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),
+    "coral_lm_load_kenlm_binary": (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),
+    "coral_lm_load": (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),
     "coral_lm_free": (_i32, [_vp]),
     "coral_lm_info": (_i32, [_vp, C.POINTER(_i32), _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "coral_lm_contains": (_i32, [_vp, _vp, _vp, _i64, _vp]),

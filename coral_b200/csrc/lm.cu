@@ -51,12 +51,21 @@ extern "C" {
 const char* coral_last_error(void) { return g_last_error.c_str(); }
 int32_t coral_abi_version(void) { return 1; }
 
-int32_t coral_lm_load_arpa(const char* path, int32_t device, coral_lm** out) {
-  if (!path || !out) return fail(CORAL_EARG, "coral_lm_load_arpa: null argument");
+static int32_t lm_load(const char* path, int32_t device, coral_lm** out, int kind);
+
+int32_t coral_lm_load_arpa(const char* path, int32_t device, coral_lm** out) { return lm_load(path, device, out, 0); }
+int32_t coral_lm_load_kenlm_binary(const char* path, int32_t device, coral_lm** out) { return lm_load(path, device, out, 1); }
+int32_t coral_lm_load(const char* path, int32_t device, coral_lm** out) {
+  if (!path || !out) return fail(CORAL_EARG, "coral_lm_load: null argument");
+  return lm_load(path, device, out, is_kenlm_binary(path) ? 1 : 0);
+}
+
+static int32_t lm_load(const char* path, int32_t device, coral_lm** out, int kind) {
+  if (!path || !out) return fail(CORAL_EARG, "coral_lm_load: null argument");
   *out = nullptr;
   coral_lm* lm = new coral_lm();
   std::string err;
-  int rc = load_arpa(path, lm->host, err);
+  int rc = kind == 1 ? load_kenlm_binary(path, lm->host, err) : load_arpa(path, lm->host, err);
   if (rc != 0) { delete lm; return fail(rc, err); }
   rc = build_lexicon(lm->host, nullptr, lm->vocab_lex, err);
   if (rc != 0) { delete lm; return fail(rc, err); }

@@ -26,6 +26,7 @@ struct HostLm {
   std::vector<NgSlot> ng;
   uint64_t ng_mask = 0;
   uint32_t bos_id = 0, eos_id = 0;
+  int kenlm_keys = 0;  // ng holds KenLM chain keys (read from a KenLM binary), see lm_tables.h
 };
 
 struct HostLexicon {
@@ -37,6 +38,11 @@ struct HostLexicon {
 
 // returns 0 on success; negative status + message otherwise
 int load_arpa(const char* path, HostLm& lm, std::string& err);
+
+// KenLM probing binary (what CoRal ships as language_model/{N}gram.bin, R:src/coral/ngram.py:361-387)
+int load_kenlm_binary(const char* path, HostLm& lm, std::string& err);
+// true if the file starts with KenLM's binary magic
+bool is_kenlm_binary(const char* path);
 
 // unigrams == nullptr <=> pyctcdecode's ``unigrams=None`` (no unigram set, no char trie)
 int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams, HostLexicon& out,
@@ -58,6 +64,7 @@ inline LmView make_view(const HostLm& lm, const HostLexicon& lx, const UniEntry*
   v.bos_id = lm.bos_id;
   v.eos_id = lm.eos_id;
   v.has_unigrams = lx.has_unigrams;
+  v.kenlm_keys = lm.kenlm_keys;
   v.present = 1;
   return v;
 }

@@ -10,9 +10,9 @@
 //   uni[wid]      8 B   {float prob, float backoff}        direct-indexed by word id (0 = <unk>)
 //   ng[slot]     16 B   {u64 chain key, float prob, float backoff}   ONE open-addressing
 //                       table for all orders >= 2, linear probing, load <= 0.5, key 0 = empty.
-//                       chain key of "c2 c1 w" = push(push(push(seed, w), c1), c2): the same
-//                       incremental order KenLM's probing model hashes in, so a longest-match
-//                       lookup extends one probe per context word and stops at the first miss.
+//                       chain key of "c2 c1 w" = combine(combine(id(w), c1), c2): KenLM's probing
+//                       keys, built in the order a longest-match lookup extends them (one probe
+//                       per context word, stop at the first miss).
 //   lex[slot]    16 B   {u64 word hash, u32 word id, u32 flags}      every prefix of every
 //                       word of (LM vocabulary U unigram list); rolling hash over code points.
 //
@@ -70,6 +70,7 @@ struct LmView {
   uint32_t bos_id;
   uint32_t eos_id;
   int32_t has_unigrams;  // len(unigram_set) > 0 after filtering with the LM vocabulary
+  int32_t kenlm_keys;    // informational: the tables came from a KenLM binary (keys are KenLM's either way)
   int32_t present;       // 0 => decoder built without a language model
 };
 
@@ -83,7 +84,6 @@ CORAL_HD uint64_t mix64(uint64_t x) {
 }
 
 constexpr uint64_t kWordHashSeed = 0x243F6A8885A308D3ULL;
-constexpr uint64_t kNgSeed = 0x13198A2E03707344ULL;
 
 // rolling hash of a word, one Unicode code point at a time
 // Incremental hashes sit on dependent chains of the beam kernel's critical path, so each
@@ -95,7 +95,16 @@ CORAL_HD uint64_t hash_step(uint64_t h, uint64_t x) {
   return h ? h : 1;  // 0 is the empty-slot marker
 }
 CORAL_HD uint64_t word_hash_push(uint64_t h, uint32_t cp) { return hash_step(h, (uint64_t)cp); }
-CORAL_HD uint64_t ng_key_push(uint64_t k, uint32_t w) { return hash_step(k, (uint64_t)w); }
+// n-gram identity = KenLM's own chain hash (UP:kenlm lm/search_hashed.hh, CombineWordHash): the
+// predicted word's id, then one multiply-xor per context word, most recent first. A model read
+// from a KenLM probing binary only has these keys (the words of an n-gram are not stored), so
+// ARPA-built tables use the same scheme and the kernel has one way to form a key.
+CORAL_HD uint64_t kenlm_combine(uint64_t k, uint32_t w) {
+  return (k * 8978948897894561157ULL) ^ ((uint64_t)(1u + w) * 17894857484156487943ULL);
+}
+// one key scheme for every model (no per-probe branch in the kernel): KenLM's
+CORAL_HD uint64_t ng_key_first(const LmView&, uint32_t w) { return (uint64_t)w; }
+CORAL_HD uint64_t ng_key_next(const LmView&, uint64_t k, uint32_t w) { return kenlm_combine(k, w); }
 
 CORAL_HD bool lex_find(const LmView& lm, uint64_t h, uint32_t& wid, uint32_t& flags) {
   uint64_t i = (h >> 20) & lm.lex_mask;
@@ -153,10 +162,10 @@ CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, Lm
 #if defined(__CUDA_ARCH__)
   {
     // first pass: every order's slot is prefetched into L1 (the keys depend only on the words)
-    uint64_t kp = ng_key_push(kNgSeed, w);
+    uint64_t kp = ng_key_first(lm, w);
 #pragma unroll 1
     for (uint32_t i = 0; i < nctx; ++i) {
-      kp = ng_key_push(kp, in.w[i]);
+      kp = ng_key_next(lm, kp, in.w[i]);
       asm volatile("prefetch.global.L1 [%0];" ::"l"(lm.ng + ((kp >> 20) & lm.ng_mask)));
     }
   }
@@ -167,12 +176,12 @@ CORAL_HD float lm_base_score(const LmView& lm, const LmState& in, uint32_t w, Lm
   out.b[0] = u.backoff;
   uint32_t olen = 1;
   uint32_t ngram_len = 1;
-  uint64_t key = ng_key_push(kNgSeed, w);
+  uint64_t key = ng_key_first(lm, w);
   int np = 1;
 #pragma unroll 1
   for (uint32_t i = 0; i < nctx; ++i) {
     const int n = (int)i + 2;
-    key = ng_key_push(key, in.w[i]);
+    key = ng_key_next(lm, key, in.w[i]);
     float p, b;
     ++np;
     if (!ng_find(lm, key, p, b)) break;

@@ -41,19 +41,16 @@ def _current_device() -> int:
 
 
 class KenlmModel:
-    """``kenlm.Model``: an ARPA file parsed on the host and held as hash tables in HBM."""
+    """``kenlm.Model``: an ARPA file or a KenLM probing binary (told apart by the magic bytes, as
+    KenLM does) read on the host and held as hash tables in HBM."""
 
     def __init__(self, path: str, device: int | None = None):
         path = os.fspath(path)
-        if path.endswith(".bin") or path.endswith(".binary"):
-            raise NotImplementedError(
-                "KenLM binary files are not readable yet (SURVEY.md section 8f N1); pass the ARPA file"
-            )
         self.path = path
         self.device = _current_device() if device is None else device
         lib = _lib.load()
         h = C.c_void_p()
-        _lib.check(lib.coral_lm_load_arpa(path.encode(), self.device, C.byref(h)))
+        _lib.check(lib.coral_lm_load(path.encode(), self.device, C.byref(h)))
         self._h = h
         order = C.c_int32()
         counts = (C.c_uint64 * 8)()

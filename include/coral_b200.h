@@ -48,6 +48,13 @@ int32_t coral_abi_version(void);
  * R:src/coral/ngram.py:341-343 via pyctcdecode.build_ctcdecoder(kenlm_model_path=...)).
  * Parses on the host and uploads the tables to `device`. */
 int32_t coral_lm_load_arpa(const char* path, int32_t device, coral_lm** out);
+/* The same from a KenLM *probing* binary (what CoRal ships as language_model/{N}gram.bin,
+ * R:src/coral/ngram.py:361-387). The reader is a restatement of the published format that no real
+ * build_binary output was available to check: it accepts a file only if every
+ * structural invariant holds and refuses trie / quantised models by name (CORAL_EIO). */
+int32_t coral_lm_load_kenlm_binary(const char* path, int32_t device, coral_lm** out);
+/* kenlm.Model(path): ARPA or KenLM binary, told apart by the magic bytes. */
+int32_t coral_lm_load(const char* path, int32_t device, coral_lm** out);
 int32_t coral_lm_free(coral_lm* lm);
 /* kenlm.Model.order, n-gram counts per order [order], vocabulary size, HBM bytes. */
 int32_t coral_lm_info(const coral_lm* lm, int32_t* order, uint64_t* ngram_counts, uint64_t* vocab_size,

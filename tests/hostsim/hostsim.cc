@@ -46,7 +46,8 @@ void* hs_create(const char* arpa_path, const uint32_t* label_cps, const int32_t*
     for (int q = 0; q < n; ++q) d->P.label_cps[v][q] = label_cps[label_off[v] + q];
   }
   if (arpa_path) {
-    if (load_arpa(arpa_path, d->lm, g_err) != 0) { delete d; return nullptr; }
+    const int rc = is_kenlm_binary(arpa_path) ? load_kenlm_binary(arpa_path, d->lm, g_err) : load_arpa(arpa_path, d->lm, g_err);
+    if (rc != 0) { delete d; return nullptr; }
     std::vector<std::u32string> uni;
     if (n_uni >= 0) {
       for (int64_t i = 0; i < n_uni; ++i)

@@ -4,6 +4,8 @@ transcripts identical with scores within 1e-4 relative (the tolerance BASELINE.j
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pytest
 
@@ -496,6 +498,36 @@ def test_pipeline_on_device_handoff(gpu_decoder, oracle_decoder, torch_cuda, tmp
     assert [g["chunks"] for g in got] == [r["chunks"] for r in ref]
     one = ours(audios[1].copy(), decoder_kwargs={"beam_width": 20})
     assert one["text"] == stock(audios[1].copy(), decoder_kwargs={"beam_width": 20})["text"]
+
+
+def test_kenlm_binary_model_directory(gpu_decoder, oracle_decoder, small_lm, small_workload, tmp_path):
+    """a decoder directory in CoRal's shipped layout -- language_model/{N}gram.bin
+    (KenLM probing binary) + unigrams.txt + attrs.json (R:src/coral/ngram.py:361-387) -- loads through
+    load_from_dir and decodes exactly like the ARPA-built decoder."""
+    import shutil
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from kenlm_binary_writer import write_probing_binary
+
+    from coral_b200.decoder import BeamSearchDecoderCTC
+    from oracle.arpa import ArpaModel
+
+    d = tmp_path / "model"
+    gpu_decoder.save_to_dir(str(d))
+    lm_dir = d / "language_model"
+    arpa = [f for f in os.listdir(lm_dir) if f.endswith(".arpa")]
+    assert len(arpa) == 1
+    write_probing_binary(ArpaModel.load(str(lm_dir / arpa[0])), str(lm_dir / "5gram.bin"))
+    os.remove(lm_dir / arpa[0])
+    dec = BeamSearchDecoderCTC.load_from_dir(str(d))
+    assert dec._language_model._kenlm_model.order == gpu_decoder._language_model._kenlm_model.order
+    w = small_workload
+    lg = [w.logits[u, : w.lengths[u]] for u in range(6)]
+    got = dec.decode_beams_batch(None, lg)
+    for x, g in zip(lg, got):
+        beams_equal(oracle_decoder.decode_beams(x), g)
+    shutil.rmtree(d)
 
 
 # ------------------------------------------------------------------- golden fixtures on GPU
