@@ -66,10 +66,10 @@ constexpr int min_ctas() {
   return m < 1 ? 1 : (m < by_regs ? m : by_regs);
 }
 
-template <int NT, int BW, int OUTC, bool FRAMES>
+template <int NT, int BW, int OUTC, bool FRAMES, bool STATS>
 __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_search_kernel(const __grid_constant__ BeamLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
+  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES, STATS>;
   typename Dec::Sm& sm = *reinterpret_cast<typename Dec::Sm*>(smem_raw);
   const uint32_t slot = blockIdx.x;
   SlotScratch sc;
@@ -139,11 +139,11 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_sea
   }
 }
 
-template <int NT, int BW, int OUTC, bool FRAMES = false>
-static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStream_t st) {
-  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES>;
+template <int NT, int BW, int OUTC, bool FRAMES, bool STATS>
+static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStream_t st) {
+  using Dec = BeamDecoder<NT, BW, OUTC, FRAMES, STATS>;
   const size_t smem = sizeof(typename Dec::Sm);
-  auto kern = beam_search_kernel<NT, BW, OUTC, FRAMES>;
+  auto kern = beam_search_kernel<NT, BW, OUTC, FRAMES, STATS>;
   // occupancy of this instantiation, queried once per device (the runtime calls are not free
   // and this function sits on the latency path of small batches)
   static int per_sm_cache[64] = {0};
@@ -230,6 +230,13 @@ static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStr
   kern<<<grid, NT, smem, st>>>(L);
   CORAL_CUDA_OK(cudaGetLastError());
   return CORAL_OK;
+}
+
+// the instantiation with work counters and cycle timers only when the caller passes a stats buffer
+template <int NT, int BW, int OUTC, bool FRAMES = false>
+static int32_t launch_beam(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaStream_t st) {
+  if (L.stats) return launch_beam_t<NT, BW, OUTC, FRAMES, true>(dec, L, B, st);
+  return launch_beam_t<NT, BW, OUTC, FRAMES, false>(dec, L, B, st);
 }
 
 }  // namespace coral

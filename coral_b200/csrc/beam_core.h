@@ -408,9 +408,12 @@ struct PhaseTimer {
   }
 };
 
-template <int NT, int BW, int OUTC, bool FRAMES = false>
+template <int NT, int BW, int OUTC, bool FRAMES = false, bool STATS = true>
 struct BeamDecoder {
   using Sm = GroupShared<BW, OUTC, FRAMES>;
+  // work counters and cycle timers exist only in the STATS instantiation: in the default one
+  // this is a compile-time null and everything that hangs off it folds away
+  static CORAL_DEV unsigned long long* stats_of(const UttIO& io) { return STATS ? io.stats : nullptr; }
 
   // candidate descriptor: representative beam, the LAST member beam (pyctcdecode keeps the
   // later candidate's tuple on a merge -- its frames), token, kind/flags
@@ -763,7 +766,7 @@ struct BeamDecoder {
     {
       {
 #if defined(__CUDA_ARCH__)
-        const bool tim = io.stats != nullptr;  // tuning: where a letter item spends its cycles
+        const bool tim = stats_of(io) != nullptr;  // tuning: where a letter item spends its cycles
         const long long tA = tim ? clock64() : 0;
         long long tB = 0, tC = 0, tD = 0;
 #endif
@@ -836,10 +839,10 @@ struct BeamDecoder {
             const bool in_lm = (fl_m & kInLm) != 0;
             const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
             BndRec nr;
-            CORAL_OP_T0(io.stats != nullptr);
+            CORAL_OP_T0(stats_of(io) != nullptr);
             const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][rb]].st, in_lm ? sm.wid[cur][rb] : 0u, oov,
-                                            false, nr.st, io.stats ? sm.cnt : nullptr);
-            CORAL_OP_T1(io.stats != nullptr, sm, 1);
+                                            false, nr.st, stats_of(io) ? sm.cnt : nullptr);
+            CORAL_OP_T1(stats_of(io) != nullptr, sm, 1);
             nr.lm_raw = d_add(sm.lm_raw[cur][rb], sw);
             raw_new = nr.lm_raw;
             sc.bnd[bnd_new] = nr;
@@ -856,9 +859,9 @@ struct BeamDecoder {
               unsigned long long h = sm.whash[cur][rb];
               for (int qq = 0; qq < P.label_ncp[c]; ++qq) h = word_hash_push(h, P.label_cps[c][qq]);
               uint32_t lw, lf;
-              if (io.stats) atom_add(&sm.cnt[4], 1u);
+              if (stats_of(io)) atom_add(&sm.cnt[4], 1u);
               bool lfound;
-              { CORAL_OP_T0(io.stats != nullptr); lfound = lex_find(lm, h, lw, lf); CORAL_OP_T1(io.stats != nullptr, sm, 3); }
+              { CORAL_OP_T0(stats_of(io) != nullptr); lfound = lex_find(lm, h, lw, lf); CORAL_OP_T1(stats_of(io) != nullptr, sm, 3); }
               if (lfound) {
                 nfl = ((lf & kLexPrefixOfUnigram) ? 0u : kOovPartial) | ((lf & kLexInUnigrams) ? kInUni : 0u) |
                       ((lf & kLexInLm) ? kInLm : 0u);
@@ -899,7 +902,7 @@ struct BeamDecoder {
         // clear the other parity's per-frame counters for the next frame. This must sit behind
         // this frame's first barrier: every thread read S[q ^ 1] (the beam count) on its way in.
         sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
-        if (io.stats) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
+        if (stats_of(io)) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
       }
       // Work units = (token group g, chunk of 32 nodes); group K is the "repeat" family. A warp
       // takes whole units, so its lanes follow the same code path (same token kind) instead of
@@ -1204,17 +1207,17 @@ struct BeamDecoder {
   static CORAL_DEV void frame_step(Sm& sm, const LmView& lm, const DecodeParams& P, SlotScratch& sc,
                                    const UttIO& io, int f, int cur, int q, uint32_t nb, int t) {
     PhaseTimer pt;
-    pt.start(io.stats);
+    pt.start(stats_of(io));
     hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]], &lm, &P, &sc, f);
     pt.mark(8);
 #if defined(__CUDA_ARCH__)
     const uint32_t bnd_before = sm.bnd_count;
-    const long long t_exp = io.stats ? clock64() : 0;
+    const long long t_exp = stats_of(io) ? clock64() : 0;
 #endif
     expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
     pt.mark(9);
 #if defined(__CUDA_ARCH__)
-    if (io.stats && threadIdx.x == 0) {  // tuning: expand time split by "frame scored a word with the LM"
+    if (stats_of(io) && threadIdx.x == 0) {  // tuning: expand time split by "frame scored a word with the LM"
       const int slot = sm.bnd_count != bnd_before ? 5 : 6;
       sm.opc[slot] += (unsigned long long)(clock64() - t_exp);
       sm.opn[slot] += 1u;
@@ -1269,7 +1272,7 @@ struct BeamDecoder {
           const bool oov = !open || (lm.has_unigrams && !(lfl & kInUni)) || !in_lm;
           LmState out;
           const double sw = lm_word_score(lm, P, sc.bnd[sm.bnd[cur][last]].st, in_lm ? sm.wid[cur][last] : 0u, oov,
-                                          true, out, io.stats ? sm.cnt : nullptr);
+                                          true, out, stats_of(io) ? sm.cnt : nullptr);
           comb = d_add(logit, d_add(d_add(sm.lm_raw[cur][last], sw), 0.0));
         }
         // text node: the open-word node itself, or the parent of a closed-word node
@@ -1286,11 +1289,11 @@ struct BeamDecoder {
       if (lane == 0) {
         *io.out_n = (int32_t)nf;
         *io.out_status = sm.status;
-        if (io.stats) {
+        if (stats_of(io)) {
           sm.cnt[5] = sm.node_count;
           sm.cnt[6] = sm.bnd_count;
-          for (int k = 0; k < 8; ++k) atom_add(&io.stats[k], (unsigned long long)sm.cnt[k]);
-          for (int k = 0; k < 8; ++k) { atom_add(&io.stats[16 + k], sm.opc[k]); atom_add(&io.stats[24 + k], (unsigned long long)sm.opn[k]); }
+          for (int k = 0; k < 8; ++k) atom_add(&stats_of(io)[k], (unsigned long long)sm.cnt[k]);
+          for (int k = 0; k < 8; ++k) { atom_add(&stats_of(io)[16 + k], sm.opc[k]); atom_add(&stats_of(io)[24 + k], (unsigned long long)sm.opn[k]); }
         }
       }
       for (uint32_t r = lane; r < nf && r < (uint32_t)P.n_best; r += NT) {
@@ -1418,7 +1421,7 @@ struct BeamDecoder {
       const int nf = io.T - t0 < kChunk ? io.T - t0 : kChunk;
       {
         PhaseTimer ps;
-        ps.start(io.stats);
+        ps.start(stats_of(io));
         stage_frames(sm, P, io, t0, nf, speculate ? sc.rowsum : nullptr);
         ps.mark(15);
       }
