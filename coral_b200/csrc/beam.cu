@@ -371,6 +371,7 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.P.input_mode = input_mode;
   L.P.token_min_logp = (float)token_min_logp;
   L.P.beam_prune_logp = beam_prune_logp;
+  set_bucket_scale(L.P);
   if (dec->lm) {
     L.lm = make_view(dec->lm->host, dec->lex, dec->lm->d_uni, dec->lm->d_ng, dec->d_lex);
   } else {

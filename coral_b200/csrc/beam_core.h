@@ -132,6 +132,7 @@ struct DecodeParams {
   double beam_prune_logp;
   double alpha, beta, unk_score_offset;
   double log_base_change;  // 1 / log10(e) as the reference computes it
+  double bucket_scale;     // score buckets per unit of score (filled by set_bucket_scale on the host)
   uint32_t label_cps[kVMax][kMaxLabelCps];
   uint8_t label_ncp[kVMax];
 };
@@ -195,6 +196,10 @@ struct UttIO {
 #define CORAL_KNB 128
 #endif
 constexpr int kNB = CORAL_KNB;      // score buckets over the prune window (<= 256, multiple of 8)
+// the buckets span the prune window plus a margin; any monotone map keeps the ranking exact
+inline void set_bucket_scale(DecodeParams& P) {
+  P.bucket_scale = (double)kNB / ((P.beam_prune_logp < 0.0 ? -P.beam_prune_logp : 0.0) + 4.0);
+}
 
 // per-beam word timing (pyctcdecode's part_frames and text_frames), present only in the
 // word-frame instantiation of the kernel
@@ -691,9 +696,7 @@ struct BeamDecoder {
     const double d = d_mul(d_add(mhat, -comb), scale);
     return d >= (double)(kNB - 1) ? (uint32_t)(kNB - 1) : (d > 0.0 ? (uint32_t)d : 0u);
   }
-  static CORAL_DEV double bucket_scale(const DecodeParams& P) {
-    return d_div((double)kNB, d_add(P.beam_prune_logp < 0.0 ? -P.beam_prune_logp : 0.0, 4.0));
-  }
+  static CORAL_DEV double bucket_scale(const DecodeParams& P) { return P.bucket_scale; }
   // Candidates live in the shared-memory arrays while they fit (index < OUTC) and spill to the
   // slot's HBM buffer past that; the slow overflow path runs only if the frame really produced
   // more than OUTC candidates (flat logits / very wide beams).

@@ -185,6 +185,7 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
   P.beta = beta;
   P.unk_score_offset = unk_score_offset;
   P.log_base_change = log_base_change;
+  set_bucket_scale(P);
   switch (variant) {
     case 0: if (beam_width > 128) break; return run<32, 128, 256>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     case 1: if (beam_width > 32) break; return run<32, 32, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
