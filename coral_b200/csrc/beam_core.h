@@ -94,6 +94,13 @@ CORAL_HD double d_div(double a, double b) {
   return a / b;
 #endif
 }
+CORAL_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
 // pyctcdecode _sum_log_scores: math.log / math.exp in float64
 CORAL_HD double sum_log_scores(double s1, double s2) {
   if (s1 >= s2) return d_add(s1, log(d_add(1.0, exp(d_add(s2, -s1)))));
@@ -485,7 +492,12 @@ struct BeamDecoder {
     const int V = P.V;
     CORAL_LANES(NT) {
 #pragma unroll 2
-      for (int i = lane; i < nf * V; i += NT) sm.lp[i / V][i % V] = io.logits[(size_t)t0 * V + i];
+      // row = i / V without a runtime division: exact multiply-high for i < 2^16, V <= 64
+      const uint32_t inv_v = V > 1 ? 0xFFFFFFFFu / (uint32_t)V + 1u : 0u;
+      for (int i = lane; i < nf * V; i += NT) {
+        const uint32_t f = V > 1 ? mulhi_u32((uint32_t)i, inv_v) : (uint32_t)i;
+        sm.lp[f][(uint32_t)i - f * (uint32_t)V] = io.logits[(size_t)t0 * V + i];
+      }
 #if defined(__CUDA_ARCH__)
       // pull the next chunk of this utterance towards L2 while this one is decoded
       const int nxt0 = t0 + kChunk;
@@ -505,9 +517,10 @@ struct BeamDecoder {
     if (as_prob) {
       CORAL_LANES(NT) {
         for (int i = lane; i < nf * V; i += NT) {
-          float x = sm.lp[i / V][i % V];
+          float& cell = (&sm.lp[0][0])[(i / V) * kVMax + i % V];
+          float x = cell;
           x = x < 1e-15f ? 1e-15f : (x > 1.0f ? 1.0f : x);
-          sm.lp[i / V][i % V] = logf(x);
+          cell = logf(x);
         }
       }
       CORAL_GSYNC(NT);
@@ -916,10 +929,13 @@ struct BeamDecoder {
       const uint32_t units = ((uint32_t)K + 1u) * nchunks;
       constexpr uint32_t kWarps = NT / 32;
 #pragma unroll 1
+      uint32_t g = 0, ch = (uint32_t)lane >> 5;  // unit u = g * nchunks + ch, advanced without dividing
+      while (nchunks && ch >= nchunks) { ch -= nchunks; ++g; }
       for (uint32_t u = (uint32_t)lane >> 5; u < units; u += kWarps) {
-        const uint32_t g = u / nchunks;
-        const uint32_t j = (u - g * nchunks) * 32u + ((uint32_t)lane & 31u);
+        const uint32_t j = ch * 32u + ((uint32_t)lane & 31u);
         if (j < nN) expand_item(sm, lm, P, sc, io, f, cur, q, nb, outs, bscale, K, g == (uint32_t)K, j, g, lmax);
+        ch += kWarps;
+        while (ch >= nchunks) { ch -= nchunks; ++g; }
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
     }
