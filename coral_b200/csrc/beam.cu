@@ -21,6 +21,7 @@ struct BeamLaunch {
   const int32_t* order;
   const int32_t* ready;     // streamed input: number of utterances whose logits have landed (or NULL)
   int32_t ready_chunk;      // utterances per host->device chunk
+  long long ready_timeout;  // cycles a thread group waits for its chunk before the launch gives up
   int32_t B;
   int32_t* out_n;
   double* out_logit;
@@ -106,9 +107,10 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_sea
         const int need = min(L.B, (u / L.ready_chunk + 1) * L.ready_chunk);
         const long long t0 = clock64();
         int ok = 1;
+        volatile int32_t* gave_up = L.work + 1;  // set by the first group that timed out: nobody waits again
         while (*reinterpret_cast<const volatile int32_t*>(L.ready) < need) {
           __nanosleep(500);
-          if (clock64() - t0 > (40LL << 30)) { ok = 0; break; }
+          if (*gave_up || clock64() - t0 > L.ready_timeout) { ok = 0; *gave_up = 1; break; }
         }
         __threadfence();
         sm.status = ok;
@@ -216,8 +218,8 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
     S.outs_cap = outs_cap;
     S.wf_cap = wf_cap;
   }
-  if (!S.d_work) CORAL_CUDA_OK(cudaMalloc(&S.d_work, sizeof(int32_t)));
-  CORAL_CUDA_OK(cudaMemsetAsync(S.d_work, 0, sizeof(int32_t), st));
+  if (!S.d_work) CORAL_CUDA_OK(cudaMalloc(&S.d_work, 2 * sizeof(int32_t)));  // work counter, give-up flag
+  CORAL_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 2 * sizeof(int32_t), st));
   L.scratch = S.d_scratch;
   L.slot_bytes = S.slot_bytes;
   L.node_cap = node_cap;
@@ -390,6 +392,8 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.stats = reinterpret_cast<unsigned long long*>(stats_dev);
   L.ready = ready_dev;
   L.ready_chunk = ready_chunk > 0 ? ready_chunk : 1;
+  L.ready_timeout = 40LL << 30;  // about 20 s; CORAL_READY_TIMEOUT_CYCLES overrides (tests)
+  if (const char* e = getenv("CORAL_READY_TIMEOUT_CYCLES")) { const long long v = atoll(e); if (v > 0) L.ready_timeout = v; }
   L.out_frames = out_word_frames_dev;
   L.out_nwords = out_word_counts_dev;
   L.max_words = max_words;

@@ -432,6 +432,29 @@ def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, 
         beams_equal(oracle_decoder.decode_beams(x), g)
 
 
+def test_stalled_input_stream_fails_the_launch_instead_of_hanging(gpu_decoder, torch_cuda, small_workload, monkeypatch):
+    """A ready counter that never moves (a copier that died) must end the launch with an error
+    status for every utterance after ONE timeout, not hang the device."""
+    import time
+
+    torch = torch_cuda
+    monkeypatch.setenv("CORAL_READY_TIMEOUT_CYCLES", str(400_000_000))  # ~0.2 s
+    w = small_workload
+    d_logits = torch.from_numpy(w.logits).cuda()
+    d_len = torch.from_numpy(w.lengths).cuda()
+    ready = torch.zeros(1, dtype=torch.int32, device="cuda")
+    t0 = time.perf_counter()
+    outs = gpu_decoder.decode_launch(d_logits, d_len, None, n_best=1, ready=(ready, 4))
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 10.0
+    status = outs[5].cpu().numpy()
+    assert (status == -3).all() and (outs[0].cpu().numpy() == 0).all()
+    monkeypatch.delenv("CORAL_READY_TIMEOUT_CYCLES")
+    ok = gpu_decoder.decode_launch(d_logits, d_len, None, n_best=1)  # the decoder is fine afterwards
+    torch.cuda.synchronize()
+    assert int(ok[5].abs().sum().item()) == 0
+
+
 def test_concurrent_streams_share_one_decoder(gpu_decoder, torch_cuda, cache_dir):
     """Launches of the same decoder handle on different CUDA streams may overlap: each stream
     has its own scratch arenas and work counter (SURVEY 8b threading contract)."""
