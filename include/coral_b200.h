@@ -103,11 +103,15 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *   out_lm_score    float64 [B, n_best] combined score (pyctcdecode's "lm_score")
  *   out_tokens      uint8 [B, n_best, T_max] alphabet indices of the text (no blanks)
  *   out_lens        int32 [B, n_best]
- *   out_status      int32 [B]           0 or CORAL_ECAP for that utterance
+ *   out_status      int32 [B]           0, CORAL_ECAP (arena capacity) or CORAL_ECUDA (streamed
+ *                                       input never arrived) for that utterance
  *   stats_dev       uint64 [32] or NULL: beam extensions, LM word scorings, n-gram probes,
- *                   frames, lexicon probes, trie nodes, LM boundary records, child-table
- *                   growths (work counters of SURVEY 8d); [8..15] = cycles per kernel phase,
- *                   [16..23] / [24..31] = cycles / calls of selected device operations (tuning)
+ *                   frames, lexicon probes, back-pointer records, LM boundary records, frames that
+ *                   needed the radix select (work counters of SURVEY 8d); [8..15] = cycles per
+ *                   kernel phase, [16..23] / [24..31] = cycles / calls of selected device
+ *                   operations (tuning). A non-NULL buffer selects the instrumented
+ *                   instantiation of the kernel, which is about twice as slow: pass NULL unless
+ *                   the counters are wanted.
  *   ready_dev       int32 device scalar or NULL. Streamed input: the kernel may be launched
  *                   while the logits are still being copied in utterance order on ANOTHER
  *                   stream, ready_chunk utterances at a time; after each chunk the copier stores
