@@ -115,7 +115,36 @@ def greedy_decode(logits, vocab: CTCVocabulary, lengths=None, pad_fixup: bool = 
     d_logits = _to_device(logits, torch.float32)
     d_len = _to_device(lengths, torch.int32) if lengths is not None else None
     _, tokens, lens = greedy_decode_device(d_logits, d_len, vocab.pad_id, pad_fixup)
-    return vocab.to_strings(tokens.cpu().numpy(), lens.cpu().numpy())
+    return _device_rows_to_strings(tokens, lens, vocab)
+
+
+def _device_rows_to_strings(tokens, lens, vocab: CTCVocabulary) -> list[str]:
+    """Collapsed id rows still on the device -> strings: the vocabulary lookup and the compaction
+    run on the GPU and one flat code-point buffer comes back (instead of the padded ``[B, T]`` id
+    matrix); multi-character tokens that actually occur fall back to the host path."""
+    torch = _torch()
+    B, T = tokens.shape
+    dev = tokens.device
+    table = getattr(vocab, "_d_cp", None)
+    if table is None or table.device != dev:
+        table = torch.from_numpy(vocab._cp.astype(np.int64)).to(dev).to(torch.int32)
+        vocab._d_cp = table
+    l64 = lens.to(torch.int64)
+    mask = torch.arange(T, device=dev)[None, :] < l64[:, None]
+    ids = tokens[mask].to(torch.int64)
+    if ids.numel() and (int(ids.min().item()) < 0 or int(ids.max().item()) >= table.numel()):
+        return vocab.to_strings(tokens.cpu().numpy(), lens.cpu().numpy())
+    flat = table[ids]
+    if bool((flat == 0).any().item()):
+        return vocab.to_strings(tokens.cpu().numpy(), lens.cpu().numpy())
+    off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(l64, 0, out=off[1:])
+    text = flat.cpu().numpy().view(np.uint32).tobytes().decode("utf-32-le")
+    o = off.cpu().tolist()
+    out = [text[a:b].strip() for a, b in zip(o[:-1], o[1:])]
+    if vocab.do_lower_case:
+        out = [s.lower() for s in out]
+    return out
 
 
 def decode_ids(ids, vocab: CTCVocabulary, lengths=None, group_tokens: bool = True) -> list[str]:
@@ -124,4 +153,4 @@ def decode_ids(ids, vocab: CTCVocabulary, lengths=None, group_tokens: bool = Tru
     d_ids = _to_device(ids, torch.int32)
     d_len = _to_device(lengths, torch.int32) if lengths is not None else None
     tokens, lens = collapse_ids_device(d_ids, d_len, vocab.pad_id, group_tokens)
-    return vocab.to_strings(tokens.cpu().numpy(), lens.cpu().numpy())
+    return _device_rows_to_strings(tokens, lens, vocab)

@@ -38,3 +38,27 @@ print(json.dumps({"config": 4, "pairs": n, "max_len": mx, "e2e_s": round(t1, 3),
                   "GCUPS_chars_full_matrix": round(cells / res["chars"] / 1e6, 1),
                   "algorithmic_GB_per_s_chars": round(alg / res["chars"] / 1e6, 1),
                   "cer": vs.cer, "wer": vs.wer, "kept_fraction": float(vs.keep.mean())}))
+
+# ---- config 4, end-to-end leg: greedy decode of peaky logits from host memory + per-sample scores
+if os.environ.get("CORAL_VALIDATION_GREEDY", "1") != "0":
+    import tempfile
+    from coral_b200.greedy import CTCVocabulary, greedy_decode
+    vocab_tokens = [c for c in synth.CORAL_LABELS]
+    cache = os.path.join(tempfile.gettempdir(), "coral_b200_cache")
+    wl = synth.build_workload(cache, 8192, order=5, name="eval0")
+    labels = ["|" if c == " " else ("<pad>" if c == "" else ("<unk>" if c == "⁇" else c)) for c in wl.labels]
+    vocab = CTCVocabulary(labels, labels.index("<pad>"))
+    h_logits = torch.from_numpy(wl.logits).pin_memory()
+    for _ in range(2):
+        hy = greedy_decode(h_logits, vocab, lengths=wl.lengths)
+        validation_scores(hy, wl.references)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hy = greedy_decode(h_logits, vocab, lengths=wl.lengths)
+    t_dec = time.perf_counter() - t0
+    vs2 = validation_scores(hy, wl.references, max_cer=0.6)
+    t_all = time.perf_counter() - t0
+    print(json.dumps({"config": 4, "leg": "greedy decode from pinned host logits + per-sample CER/WER + keep mask",
+                      "utterances": 8192, "decode_s": round(t_dec, 4), "total_s": round(t_all, 4),
+                      "utt_per_s": round(8192 / t_all), "h2d_MB": round(h_logits.numel() * 4 / 1e6),
+                      "cer": vs2.cer, "kept_fraction": float(vs2.keep.mean())}))
