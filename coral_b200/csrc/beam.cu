@@ -207,8 +207,7 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
     S.n_slots = 0;
     const size_t bytes = sb * n_slots;
     CORAL_CUDA_OK(cudaMalloc(&S.d_scratch, bytes));
-    // nothing to initialise: every arena is written before it is read (the kernel clears the
-    // part of the child table an utterance uses)
+    // nothing to initialise: every arena record is written before it is read
     S.scratch_bytes = bytes;
     S.slot_bytes = sb;
     S.n_slots = n_slots;

@@ -749,9 +749,7 @@ struct BeamDecoder {
   // ---- phase 1: hash the live nodes of the current beam list -----------------------------
   // The hash was cleared during the previous frame's phase 3. The lane whose CAS inserts a
   // node registers it in the node list; every beam records itself in its node's slot.
-  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb, double best_lp, const LmView* lm = nullptr,
-                                   const DecodeParams* P = nullptr, const SlotScratch* sc = nullptr, int f = 0) {
-    (void)lm; (void)P; (void)sc; (void)f;
+  static CORAL_DEV void hash_beams(Sm& sm, int cur, int q, uint32_t nb, double best_lp) {
     CORAL_LANES(NT) {
       if (lane == 0) {
         // bucket reference for this frame: last frame's best score + this frame's best
@@ -1227,7 +1225,7 @@ struct BeamDecoder {
                                    const UttIO& io, int f, int cur, int q, uint32_t nb, int t) {
     PhaseTimer pt;
     pt.start(stats_of(io));
-    hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]], &lm, &P, &sc, f);
+    hash_beams(sm, cur, q, nb, (double)sm.lp[f][sm.amax[f]]);
     pt.mark(8);
 #if defined(__CUDA_ARCH__)
     const uint32_t bnd_before = sm.bnd_count;

@@ -52,11 +52,24 @@ def oracle_decoder(small_lm):
     return build_ctcdecoder(synth.CORAL_LABELS, small_lm[2])
 
 
-def beams_equal(ref_beams, got_beams, rel=1e-4):
-    """ref: oracle 5-tuples; got: (text, ..., logit, lm) with scores at [-2], [-1]."""
+def beams_equal(ref_beams, got_beams, rel=1e-4, tie=1e-5):
+    """ref: oracle 5-tuples; got: (text, ..., logit, lm) with scores at [-2], [-1].
+
+    Texts, word frames and the ORDER of the beams must agree, scores within ``rel``. One licence:
+    CUDA's expf/logf and numpy's differ in the last ulp of the float32 log-softmax, so two beams
+    whose combined scores the reference itself separates by less than ``tie`` (absolute, about ten
+    times the accumulated ulp noise of a short utterance) may come
+    out in the other order; they are matched by text and everything else is still compared."""
     assert len(ref_beams) == len(got_beams), (len(ref_beams), len(got_beams))
+    where = {g[0]: k for k, g in enumerate(got_beams)}
+    assert len(where) == len(got_beams), "duplicate transcripts in the beam list"
     for i, (r, g) in enumerate(zip(ref_beams, got_beams)):
-        assert r[0] == g[0], f"beam {i}: {r[0]!r} != {g[0]!r}"
+        if r[0] != g[0]:
+            assert r[0] in where, f"beam {i}: {r[0]!r} missing (got {g[0]!r})"
+            j = where[r[0]]
+            gap = abs(ref_beams[i][-1] - ref_beams[j][-1])
+            assert gap <= tie, f"beam {i}: {r[0]!r} != {g[0]!r} and no near-tie (gap {gap})"
+            g = got_beams[j]
         assert abs(r[-2] - g[-2]) <= rel * max(1.0, abs(r[-2])), (i, r[-2], g[-2])
         assert abs(r[-1] - g[-1]) <= rel * max(1.0, abs(r[-1])), (i, r[-1], g[-1])
         if len(g) >= 4:  # word frames travel with the beam: (word, (start_frame, end_frame))
@@ -65,6 +78,10 @@ def beams_equal(ref_beams, got_beams, rel=1e-4):
             assert rf == gf, f"beam {i} ({r[0]!r}): word frames {rf} != {gf}"
 
 
-@pytest.fixture(scope="session")
-def rng():
-    return np.random.default_rng(20261017)
+@pytest.fixture
+def rng(request):
+    """A generator per test, seeded by the test's id: the inputs of a test do not depend on which
+    other tests ran before it."""
+    import zlib
+
+    return np.random.default_rng([20261017, zlib.crc32(request.node.nodeid.encode())])

@@ -135,7 +135,7 @@ static int run_t(HsDecoder* d, const DecodeParams& P, const float* logits, int T
   sc.outs_g.child = g_child.data();
   sc.outs_g.info = g_info.data();
   int32_t status = 0;
-  // decode the same utterance n_utt_repeat times on the same slot: exercises the epoch reuse
+  // decode the same utterance n_utt_repeat times on the same slot: exercises slot reuse
   for (int rep = 0; rep < n_utt_repeat; ++rep) {
     UttIO io;
     io.logits = logits;
