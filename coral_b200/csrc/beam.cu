@@ -417,10 +417,10 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
     if (nt == 128) return launch_beam<128, 64, 192>(dec, L, B, st);
     return launch_beam<64, 64, 192>(dec, L, B, st);
   }
-  // up to 104 beams (pyctcdecode's default is 100): arrays sized so that SEVEN thread groups fit
-  // on an SM (30.8 KB of shared memory, 72 registers) -- 17.1 -> 15.5 ms against the 128-beam
-  // instantiation's six; occupancy is worth ~10 % per group here (4 / 5 / 6 / 7: 22.4 / 19.0 / 17.1 / 15.5 ms)
-  if (beam_width <= 104 && nt == 0) return launch_beam<128, 104, 256>(dec, L, B, st);
+  // up to 104 beams (pyctcdecode's default is 100): arrays sized so that EIGHT thread groups fit
+  // on an SM (27.9 KB of shared memory, 64 registers) against the 128-beam instantiation's six.
+  // Resident groups per SM 4 / 5 / 6 / 7 / 8: 22.4 / 19.0 / 17.1 / 15.5 / 15.1 ms per 8192 utterances
+  if (beam_width <= 104 && nt == 0) return launch_beam<128, 104, 208>(dec, L, B, st);
   if (beam_width <= 128) {
     if (nt == 32) return launch_beam<32, 128, 320>(dec, L, B, st);
     if (nt == 64) return launch_beam<64, 128, 320>(dec, L, B, st);

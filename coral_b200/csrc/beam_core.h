@@ -24,6 +24,7 @@
 // nvcc it is the kernel body; compiled with -DCORAL_HOSTSIM (tests/hostsim only) the lane
 // loop runs sequentially on the CPU so the algorithm can be checked without a GPU.
 #pragma once
+#include <stddef.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -114,7 +115,10 @@ CORAL_HD unsigned long long ordered_u64(double x) {
 
 // ---------------------------------------------------------------------------- parameters
 constexpr int kVMax = 64;        // alphabet size supported by this build
-constexpr int kChunk = 16;       // frames staged in shared memory per pass
+#ifndef CORAL_KCHUNK
+#define CORAL_KCHUNK 12
+#endif
+constexpr int kChunk = CORAL_KCHUNK;  // frames staged in shared memory per pass
 constexpr int kMaxLabelCps = 8;  // code points per alphabet label
 constexpr uint32_t kNone16 = 0xFFFFu;
 constexpr uint32_t kNoTok = 0xFFu;
@@ -512,8 +516,22 @@ struct BeamDecoder {
     CORAL_GSYNC(NT);
     const float lo = -34.538776f;  // float32(log(1e-15))
     const bool as_prob = P.input_mode == 2 || (P.input_mode == 0 && sm.is_prob);
-    float* rs8 = reinterpret_cast<float*>(sm.o_order);   // [kChunk][8] strided partial row sums
-    float* rem8 = reinterpret_cast<float*>(sm.o_aux);    // [kChunk][8] raw tail elements (V % 8)
+    // Staging scratch lives in the candidate arrays, which are idle between frames: one explicit
+    // layout over the contiguous block o_key .. o_info (32 bytes per candidate slot).
+    constexpr int kLanes8 = kChunk * 8;
+    static_assert(offsetof(Sm, o_info) + sizeof(uint32_t) * OUTC - offsetof(Sm, o_key) == 32u * OUTC,
+                  "candidate arrays must be contiguous");
+    static_assert(32 * OUTC >= kLanes8 * (8 + 5 * 4), "staging scratch does not fit in the candidate arrays");
+    unsigned char* scr = reinterpret_cast<unsigned char*>(sm.o_key);
+    unsigned long long* bmask = reinterpret_cast<unsigned long long*>(scr);   // [kChunk][8] keep masks
+    float* pmax = reinterpret_cast<float*>(scr + kLanes8 * 8);                // [kChunk][8] partial maxima
+    float* racc = pmax + kLanes8;                                             // [kChunk][8] exp accumulators
+    float* erem = racc + kLanes8;                                             // [kChunk][8] exp of the V % 8 tail
+    float* bval = erem + kLanes8;                                             // [kChunk][8] best value per lane
+    uint32_t* bidx = reinterpret_cast<uint32_t*>(bval + kLanes8);             // [kChunk][8] its index
+    // the raw row sums are consumed (pass 2) before bval / bidx are written (argmax pass)
+    float* rs8 = bval;                                                        // strided partial row sums
+    float* rem8 = reinterpret_cast<float*>(bidx);                             // raw tail elements (V % 8)
     if (as_prob) {
       CORAL_LANES(NT) {
         for (int i = lane; i < nf * V; i += NT) {
@@ -548,9 +566,6 @@ struct BeamDecoder {
       CORAL_GSYNC(NT);
     } else {
       // eight lanes per frame: lane j owns numpy's accumulator r[j] (elements j, j+8, ...)
-      float* pmax = reinterpret_cast<float*>(sm.o_logit);  // [kChunk][8], candidate arrays are idle here
-      float* racc = pmax + kChunk * 8;                     // [kChunk][8]
-      float* erem = racc + kChunk * 8;                     // [kChunk][8] exp of the V % 8 tail elements
       const int main_n = V - (V % 8);
       CORAL_LANES(NT) {
         for (int p = lane; p < nf * 8; p += NT) {
@@ -621,9 +636,6 @@ struct BeamDecoder {
     // scan strided elements into (best value, best index, 64-bit keep mask), then one lane per
     // frame combines them and walks the mask's set bits.
     {
-      float* bval = reinterpret_cast<float*>(sm.o_logit) + 3 * kChunk * 8;     // [kChunk][8]
-      uint32_t* bidx = reinterpret_cast<uint32_t*>(bval + kChunk * 8);         // [kChunk][8]
-      unsigned long long* bmask = sm.o_key;                                     // [kChunk][8]
       CORAL_LANES(NT) {
         for (int p = lane; p < nf * 8; p += NT) {
           const int f = p >> 3, j = p & 7;

@@ -277,6 +277,14 @@ def test_beam_search_parameters(gpu_decoder, oracle_decoder, small_workload):
         got = gpu_decoder.decode_beams_batch(None, lg, **kw)
         for x, g in zip(lg, got):
             beams_equal(oracle_decoder.decode_beams(x, **kw), g)
+    # probabilities as input in the narrow instantiations (their staging scratch is the tightest)
+    import math
+    z = lg[0].astype(np.float64)
+    p = np.exp(z - z.max(axis=1, keepdims=True))
+    p = (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+    if math.isclose(float(p.sum(axis=1).mean()), 1):
+        for bw in (16, 48):
+            beams_equal(oracle_decoder.decode_beams(p, beam_width=bw), gpu_decoder.decode_beams_batch(None, [p], beam_width=bw)[0])
     try:
         for dec in (gpu_decoder, oracle_decoder):
             dec.reset_params(alpha=0.9, beta=0.3, unk_score_offset=-4.0, lm_score_boundary=False)

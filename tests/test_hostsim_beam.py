@@ -165,6 +165,9 @@ def test_probability_inputs(sim, oracle_decoder, small_workload):
     if not math.isclose(float(p.sum(axis=1).mean()), 1):
         pytest.skip("float32 mean of the row sums is not exactly 1 for this draw")
     _check(oracle_decoder, sim, p)
+    # the small instantiations share their staging scratch with fewer candidate slots
+    _check(oracle_decoder, sim, p, beam_width=16, variant=1)
+    _check(oracle_decoder, sim, p, variant=3)
 
 
 def test_work_counters_match_oracle(sim, oracle_decoder, small_workload):
