@@ -497,7 +497,7 @@ def run_ours(args, rank, world, local_rank):
                     "audio_s_per_s": world * audio * e2e_steps / e2e_s, "steps": e2e_steps},
             "gpu_launches": 3 * args.steps,
             "kernels_per_step": ["beam_search_kernel", "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
-            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<128,128,320>",
+            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<128,104,208> (beam widths <= 104; <128,128,320> up to 128)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": alg_bytes,
