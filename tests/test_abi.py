@@ -38,6 +38,19 @@ def test_library_builds_loads_and_exports_all_declared_symbols():
     assert loaded.coral_last_error() is not None
 
 
+def test_ctypes_signatures_have_the_declared_arity():
+    """The ctypes binding (coral_b200/_lib.py) and the header agree on the number of parameters of
+    every entry point -- the ABI grew several times and a stale binding corrupts the stack silently."""
+    from coral_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "coral_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, params in re.findall(r"\b(coral_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes binding {len(_lib.SIGNATURES[name][1])}"
+
+
 def test_argument_errors_map_to_the_reference_exceptions():
     """Status codes -> the exceptions the reference's callers see; pure host paths only."""
     import pytest
