@@ -191,6 +191,7 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
     case 1: if (beam_width > 32) break; return run<32, 32, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     case 2: if (beam_width > 512) break; return run<128, 512, 1024>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     case 3: if (beam_width > 128) break; return run<64, 128, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 4: if (beam_width > 104) break; return run<128, 104, 208>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);  // the production default
     default: break;
   }
   g_err = "unsupported variant / beam width";

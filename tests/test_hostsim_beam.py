@@ -52,7 +52,7 @@ def test_lm_sentence_scores_bit_exact(sim, oracle_decoder, small_lm, rng):
         assert oov.tolist() == [int(w not in m) for w in ws]
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 def test_peaky_utterances(sim, oracle_decoder, small_workload, variant):
     w = small_workload
     for u in range(6):
@@ -76,6 +76,7 @@ def test_flat_logits_overflow_and_trim(sim, oracle_decoder, rng):
     _check(oracle_decoder, sim, flat)                              # overflow path (4k candidates / frame)
     _check(oracle_decoder, sim, flat, beam_width=16, variant=1)
     _check(oracle_decoder, sim, flat, variant=3)                   # small shared-memory candidate arrays
+    _check(oracle_decoder, sim, flat, variant=4)                   # the production default <128, 104, 208>
     _check(oracle_decoder, sim, flat[:24], beam_width=512, variant=2)
     _check(oracle_decoder, sim, flat[:30], beam_width=300, token_min_logp=-3.0, variant=2)
 
