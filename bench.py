@@ -213,7 +213,7 @@ class ClockSampler:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from coral_b200 import synth
+    import synth
 
     n_procs = os.cpu_count() or 1
     sample = args.cpu_sample or 16 * n_procs
@@ -266,7 +266,8 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from coral_b200 import metrics, synth
+    import synth
+    from coral_b200 import metrics
     from coral_b200.decoder import build_ctcdecoder
     from coral_b200.textio import encode_utf32
 

@@ -192,6 +192,11 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
     case 2: if (beam_width > 512) break; return run<128, 512, 1024>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     case 3: if (beam_width > 128) break; return run<64, 128, 128>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     case 4: if (beam_width > 104) break; return run<128, 104, 208>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);  // the production default
+    // the other production instantiations (coral_b200/csrc/beam.cu: coral_ctc_beam_decode)
+    case 5: if (beam_width > 256) break; return run<256, 256, 640>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 6: if (beam_width > 512) break; return run<256, 512, 1280>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 7: if (beam_width > 128) break; return run<128, 128, 320>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
+    case 8: if (beam_width > 64) break; return run<64, 64, 192>(d, P, logits, T, is_prob, out_n, out_logit, out_comb, out_tokens, out_len, stats, repeat, fo);
     default: break;
   }
   g_err = "unsupported variant / beam width";

@@ -5,7 +5,7 @@ import json, os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it uses the oracle as checker)
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from coral_b200 import synth
+import synth
 from coral_b200.decoder import build_ctcdecoder
 from oracle.beam import build_ctcdecoder as oracle_build
 

@@ -24,7 +24,7 @@ def torch_cuda():
 
 @pytest.fixture(scope="module")
 def gpu_decoder(small_lm, torch_cuda):
-    from coral_b200 import synth
+    import synth
     from coral_b200.decoder import build_ctcdecoder
 
     return build_ctcdecoder(synth.CORAL_LABELS, small_lm[2])
@@ -217,7 +217,7 @@ def test_get_score_df_and_validation(torch_cuda, rng):
 
 # ---------------------------------------------------------------------------------- LM
 def test_device_lm_scores_bit_exact(gpu_decoder, oracle_decoder, small_lm, rng):
-    from coral_b200 import synth
+    import synth
 
     words, model, _ = small_lm
     flat, lens = model.sample(300, "lmtest")
@@ -257,7 +257,7 @@ def test_beam_search_peaky_all_beams(gpu_decoder, oracle_decoder, small_workload
 
 @pytest.mark.parametrize("beam_width,T", [(16, 80), (100, 60), (200, 40), (512, 24)])
 def test_beam_search_flat_logits_trim_path(gpu_decoder, oracle_decoder, rng, beam_width, T):
-    from coral_b200 import synth
+    import synth
 
     lg = [synth.flat_logits(T, rng), synth.flat_logits(max(1, T // 2), rng)]
     got = gpu_decoder.decode_beams_batch(None, lg, beam_width=beam_width)
@@ -297,7 +297,7 @@ def test_beam_search_parameters(gpu_decoder, oracle_decoder, small_workload):
 
 
 def test_beam_search_no_lm_edge_cases_and_errors(torch_cuda, small_workload, rng):
-    from coral_b200 import synth
+    import synth
     from coral_b200.decoder import build_ctcdecoder
     from oracle.beam import build_ctcdecoder as oracle_build
 
@@ -347,7 +347,7 @@ def test_hf_processor_with_lm_drop_in(gpu_decoder, oracle_decoder, small_workloa
     multiprocessing.set_start_method("spawn", force=True)
     from transformers import Wav2Vec2CTCTokenizer, Wav2Vec2FeatureExtractor, Wav2Vec2ProcessorWithLM
 
-    from coral_b200 import synth
+    import synth
 
     vocab = {c: i for i, c in enumerate(synth.CORAL_LABELS[:42])}
     (tmp_path / "vocab.json").write_text(json.dumps(vocab))
@@ -391,7 +391,7 @@ def test_full_size_properties(gpu_decoder, torch_cuda, cache_dir, rng):
     """Size-independent properties at a larger batch: determinism across launches and slot
     reuse, n_best=1 equals the head of the full beam list, identical inputs give identical
     outputs wherever they sit in the batch."""
-    from coral_b200 import synth
+    import synth
 
     w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
     a = gpu_decoder.decode_padded(w.logits, w.lengths, n_best=1, collect_stats=True)
@@ -412,7 +412,8 @@ def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, 
     vs-logits detection is per utterance inside the kernel (a mixed batch)."""
     import math
 
-    from coral_b200 import decoder as dmod, synth
+    import synth
+    from coral_b200 import decoder as dmod
 
     torch = torch_cuda
     w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
@@ -466,7 +467,7 @@ def test_stalled_input_stream_fails_the_launch_instead_of_hanging(gpu_decoder, t
 def test_concurrent_streams_share_one_decoder(gpu_decoder, torch_cuda, cache_dir):
     """Launches of the same decoder handle on different CUDA streams may overlap: each stream
     has its own scratch arenas and work counter (SURVEY 8b threading contract)."""
-    from coral_b200 import synth
+    import synth
 
     torch = torch_cuda
     w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
@@ -501,7 +502,7 @@ def test_pipeline_on_device_handoff(gpu_decoder, oracle_decoder, torch_cuda, tmp
     from transformers import (AutomaticSpeechRecognitionPipeline, Wav2Vec2Config, Wav2Vec2CTCTokenizer,
                               Wav2Vec2FeatureExtractor, Wav2Vec2ForCTC, pipeline)
 
-    from coral_b200 import synth
+    import synth
     from coral_b200.pipeline import BatchedCTCWithLMPipeline
 
     torch = torch_cuda
@@ -615,7 +616,7 @@ def test_config4_validation_properties_at_scale(torch_cuda, rng):
     """Config 4 shape (per-sample CER filter) at 50k pairs through size-independent properties:
     S + D + H == len(ref), I - D == len(hyp) - len(ref), identical pairs score zero, the
     aggregate equals the sum of the per-sample counts, and a 2k subsample is bit-exact."""
-    from coral_b200 import synth
+    import synth
     from coral_b200.metrics import edit_counts
     from coral_b200.validation import validation_scores
     from oracle import edit as oe

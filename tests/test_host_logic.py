@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_alphabet_normalisation_matches_oracle_and_coral_labels():
-    from coral_b200 import synth
+    import synth
     from coral_b200.alphabet import Alphabet
     from oracle.beam import Alphabet as OracleAlphabet
 
@@ -65,7 +65,7 @@ def test_shims_resolve_to_this_package():
 
 def test_decoder_object_surface_without_gpu():
     """Construction, parameter plumbing and argument errors need no GPU."""
-    from coral_b200 import synth
+    import synth
     from coral_b200.decoder import BeamSearchDecoderCTC, build_ctcdecoder
 
     dec = build_ctcdecoder(synth.CORAL_LABELS)

@@ -32,7 +32,7 @@ def _check(dec, hs, lg, **kw):
 
 
 def test_lm_sentence_scores_bit_exact(sim, oracle_decoder, small_lm, rng):
-    from coral_b200 import synth
+    import synth
 
     words, model, _ = small_lm
     m = oracle_decoder._language_model._kenlm_model
@@ -70,7 +70,7 @@ def test_parameter_sweep(sim, oracle_decoder, small_workload):
 
 
 def test_flat_logits_overflow_and_trim(sim, oracle_decoder, rng):
-    from coral_b200 import synth
+    import synth
 
     flat = synth.flat_logits(50, rng)
     _check(oracle_decoder, sim, flat)                              # overflow path (4k candidates / frame)
@@ -96,7 +96,7 @@ def test_bunched_and_tied_scores_take_the_radix_select(sim, oracle_decoder, rng)
 def test_word_frames_match_the_oracle(sim, oracle_decoder, small_workload, rng):
     """text_frames of every final beam (pyctcdecode's word time offsets): peaky utterances,
     flat logits (merges pick the later member's frames), trailing open word, leading space."""
-    from coral_b200 import synth
+    import synth
 
     w = small_workload
     cases = [w.logits[u, : w.lengths[u]] for u in range(5)] + [synth.flat_logits(40, rng), w.logits[0, :7],
@@ -118,7 +118,7 @@ def test_word_frames_match_the_oracle(sim, oracle_decoder, small_workload, rng):
 
 def test_long_flat_utterance_many_prefixes(sim, oracle_decoder, rng):
     """Thousands of distinct prefixes in one utterance (back-pointer arena, slot reuse)."""
-    from coral_b200 import synth
+    import synth
 
     lg = synth.flat_logits(120, rng)
     _check(oracle_decoder, sim, lg, beam_width=100, repeat=2)
@@ -136,7 +136,7 @@ def test_edge_cases(sim, oracle_decoder, small_workload):
 
 
 def test_no_lm_and_unigram_variants(small_lm, small_workload, rng):
-    from coral_b200 import synth
+    import synth
     from hostsim_lib import HostSim
     from oracle.arpa import ArpaModel
     from oracle.beam import Alphabet, BeamSearchDecoderCTC, build_ctcdecoder
@@ -204,3 +204,45 @@ def test_pairwise_sum_is_numpys_float32_order(rng):
             want = np.add.reduce(a) if n else np.float32(0)
             got = lib.hs_pairwise_sum(a.ctypes.data, n)
             assert np.float32(got) == np.float32(want), (n, got, want)
+
+
+# ---- the named BASELINE configs through the production instantiations (tests/cells.py) --------
+def _variant_for(beam_width):
+    # coral_b200/csrc/beam.cu: text-only instantiation per beam width
+    return 1 if beam_width <= 32 else 8 if beam_width <= 64 else 4 if beam_width <= 104 else \
+        7 if beam_width <= 128 else 5 if beam_width <= 256 else 6
+
+
+@pytest.mark.parametrize("cell,utts", [
+    ("c2flat", (10, 15)), ("c3_tml20", (15,)), ("c3flat_tml3", (14, 15)), ("c3flat_tml5", (15,)),
+    ("c5_o3_b16", (0, 8)), ("c5_o4_b64", (0, 8)), ("c5_o5_b128", (0, 8)), ("c5_o6_b256", (0, 8)),
+    ("c5_o5_b512", (0, 8)), ("c3_tml5", (0,)), ("c3_tml10", (15,))])
+def test_config_cells_device_logic(cell, utts):
+    """Kernel logic (host simulation) == oracle on utterances of the config cells, all beams, text
+    and word frames; also pins the committed cell goldens to the live inputs."""
+    import cells
+    from hostsim_lib import HostSim
+    from oracle.beam import Alphabet
+
+    labels, arpa, logits, kw = cells.cell_inputs(cell)
+    if cell in cells.CACHED:
+        data = cells.load_cache(cell)
+        assert data is not None and data["fingerprint"] == cells.fingerprint(cell), \
+            f"tests/golden/cells/{cell}.json.gz is stale: re-run tests/golden/make_cells.py"
+        ref_all = [[(t, None, [(w, (a, b)) for w, (a, b) in fr], ls, cs) for t, fr, ls, cs in utt]
+                   for utt in data["beams"]]
+        ref = [ref_all[u] for u in utts]
+    else:
+        live = cells.live_oracle(cell, which=utts, n_procs=1)
+        ref = [[(t, None, [(w, (a, b)) for w, (a, b) in fr], ls, cs) for t, fr, ls, cs in utt] for utt in live]
+    key = ("cells", arpa)
+    if key not in _SIMS:
+        _SIMS[key] = HostSim(Alphabet.build_alphabet(list(labels)).labels, arpa)
+    hs = _SIMS[key]
+    for u, r in zip(utts, ref):
+        for frames in (False, True):
+            got = hs.decode_beams(logits[u], variant=_variant_for(kw["beam_width"]), frames=frames, **kw)
+            beams_equal(r, got)
+
+
+_SIMS = {}

@@ -35,7 +35,7 @@ def test_murmur_and_bucket_rule():
 
 
 def test_binary_scores_bit_exact_and_decodes_identically(small_bin, small_lm, oracle_decoder, small_workload, rng):
-    from coral_b200 import synth
+    import synth
     from hostsim_lib import HostSim
 
     words, model, arpa = small_lm

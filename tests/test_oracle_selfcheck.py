@@ -9,7 +9,7 @@ from oracle import selfcheck
 
 @pytest.mark.skipif(not selfcheck.real_packages_available(), reason="pyctcdecode/kenlm/jiwer are not installed here")
 def test_oracle_matches_the_real_packages(small_lm, small_workload):
-    from coral_b200 import synth
+    import synth
 
     rng = np.random.default_rng(5)
     pairs = [("ab", "ba"), ("abc", "bcd"), ("hej med dig", "hej  med   dig"), ("a b c d", "a x c")]

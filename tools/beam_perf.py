@@ -3,7 +3,7 @@ import argparse, os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from coral_b200 import synth
+import synth
 from coral_b200.decoder import build_ctcdecoder
 
 ap = argparse.ArgumentParser()

@@ -3,7 +3,8 @@ import os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from coral_b200 import synth, metrics
+import synth
+from coral_b200 import metrics
 from coral_b200.decoder import build_ctcdecoder
 cache = os.path.join(tempfile.gettempdir(), "coral_b200_cache")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192

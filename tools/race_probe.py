@@ -3,7 +3,7 @@ import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from coral_b200 import synth
+import synth
 from coral_b200.decoder import build_ctcdecoder
 cache = os.path.join(tempfile.gettempdir(), "coral_b200_cache")
 w = synth.build_workload(cache, 4, order=4, n_words=2000, n_sent=5000, name="t")

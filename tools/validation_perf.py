@@ -5,7 +5,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from coral_b200 import synth, metrics
+import synth
+from coral_b200 import metrics
 from coral_b200.textio import encode_utf32
 from coral_b200.validation import validation_scores
 
