@@ -238,7 +238,9 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 log-probs / f64 scores / int32 counts",
         "data": "synthetic",
-        "config": workload_config(args, sample, "bounded sample of the same workload; CPU only"),
+        "config": dict(workload_config(args, sample, "bounded sample of the same workload; CPU only"),
+                       sample_of={"utterances_per_step": sample, "of_utterances_per_step_in_the_gpu_arm": args.utts,
+                                  "same_generator_and_seed": True}),
         "audio_s_per_s": audio * args.steps / total,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_procs, "kind": "port",
                          "sample": f"{sample} utterances per step, fork pool of {n_procs} processes over utterances "
@@ -262,6 +264,23 @@ def workload_config(args, utts, note):
 
 
 # ------------------------------------------------------------------------------ our arm
+def oracle_counts_sample(wl, beam, n_procs, sample):
+    """Oracle pass on the first ``sample`` utterances: (seconds, stats, hyps). Its cache-miss counts
+    (n_score, probes, n_partial) define the algorithmic bytes of the beam kernel at EVERY N
+     and its transcripts are the parity gate."""
+    idx = list(range(sample))
+    pool = make_pool(wl, n_procs)
+    try:
+        cpu_reference_pass(wl, idx[:n_procs], beam, n_procs, pool)  # warm the workers
+        dt, stats, hyps = cpu_reference_pass(wl, idx, beam, n_procs, pool)
+    finally:
+        pool.close()
+        pool.join()
+    stats["sample"] = sample
+    stats["hyps"] = hyps
+    return dt, stats
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -271,42 +290,44 @@ def run_ours(args, rank, world, local_rank):
     from coral_b200.decoder import build_ctcdecoder
     from coral_b200.textio import encode_utf32
 
-    # ---- CPU baseline first (rank 0, N = 1 only), before this process touches CUDA
+    # ---- CPU side first (rank 0), before this process touches CUDA: the oracle sample gives the
+    # parity gate, the algorithmic-byte counts and (N = 1 only) the reported CPU baseline
     cpu_baseline = None
     oracle_stats = None
     wl = synth.build_workload(CACHE, args.utts, order=args.order, kind=args.kind, shape=args.shape,
                               name=f"eval{rank}")
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         n_procs = os.cpu_count() or 1
-        sample = args.cpu_sample or 16 * n_procs
+        sample = args.cpu_sample or (16 * n_procs if world == 1 else 4 * n_procs)
         sample = min(sample, args.utts)
-        idx = list(range(sample))
-        pool = make_pool(wl, n_procs)
-        try:
-            cpu_reference_pass(wl, idx[:n_procs], args.beam, n_procs, pool)  # warm the workers
-            dt, oracle_stats, cpu_hyps = cpu_reference_pass(wl, idx, args.beam, n_procs, pool)
-        finally:
-            pool.close()
-            pool.join()
-        _oracle_init(wl.labels, wl.arpa_path)
-        t0 = time.perf_counter()
-        seq_n = min(sample, 2 * n_procs)
-        for u in idx[:seq_n]:
-            _oracle_decode((wl.logits[u, : wl.lengths[u]], args.beam))
-        seq_rate = seq_n / (time.perf_counter() - t0)
-        cpu_baseline = {
-            "value": sample / dt, "unit": UNIT, "cores": n_procs, "kind": "port",
-            "sample": f"first {sample} utterances of the workload, fork pool of {n_procs} processes over utterances "
-                      f"(HF batch_decode regime) + cer/wer; sequential single-process regime (what evaluate() does): "
-                      f"{seq_rate:.1f} utt/s; oracle port -- pyctcdecode/kenlm/jiwer are not installable here",
-        }
-        oracle_stats["sample"] = sample
-        oracle_stats["hyps"] = cpu_hyps
+        dt, oracle_stats = oracle_counts_sample(wl, args.beam, n_procs, sample)
+        if world == 1:
+            _oracle_init(wl.labels, wl.arpa_path)
+            t0 = time.perf_counter()
+            seq_n = min(sample, 2 * n_procs)
+            for u in range(seq_n):
+                _oracle_decode((wl.logits[u, : wl.lengths[u]], args.beam))
+            seq_rate = seq_n / (time.perf_counter() - t0)
+            cpu_baseline = {
+                "value": sample / dt, "unit": UNIT, "cores": n_procs, "kind": "port",
+                "sample": f"first {sample} utterances of the workload, fork pool of {n_procs} processes over utterances "
+                          f"(HF batch_decode regime) + cer/wer; sequential single-process regime (what evaluate() does): "
+                          f"{seq_rate:.1f} utt/s; oracle port -- pyctcdecode/kenlm/jiwer are not installable here",
+            }
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # each rank keeps to its share of the host cores (eight ranks on one socket otherwise fight
+    # over the same cores for their string work)
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+    except Exception:
+        pass
 
     dec = build_ctcdecoder(wl.labels, wl.arpa_path)
     B = args.utts
@@ -319,27 +340,22 @@ def run_ours(args, rank, world, local_rank):
     r_cps, r_off = encode_utf32(refs)
     d_rcps = torch.from_numpy(r_cps.view(np.int32)).to(dev)
     d_roff = torch.from_numpy(r_off).to(dev)
-    d_rbeg, d_rend = d_roff[:-1].contiguous(), d_roff[1:].contiguous()
     ref_max_len = int(np.diff(r_off).max())
-    cp_table = torch.from_numpy(dec._cp_table.astype(np.int64)).to(dev).to(torch.int32)
-    d_hbeg = (torch.arange(B, device=dev, dtype=torch.int64) * Tm).contiguous()
     kern_ms = []
 
     def step_device(time_kernel=False):
         """Inputs resident in HBM; everything stays on the device."""
         if time_kernel:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # decode_padded: argsort of lengths (torch) + the beam-search kernel
         d_order = torch.argsort(d_len, descending=True).to(torch.int32)
         outs = dec.decode_launch(d_logits, d_len, d_order, beam_width=args.beam, n_best=1,
                                  events=(e0, e1) if time_kernel else None)
         d_n, d_logit, d_comb, d_tok, d_lens, d_status = outs
-        hyp_cps = cp_table[d_tok.view(B, Tm).to(torch.int64)]
-        d_hend = d_hbeg + d_lens.view(B).to(torch.int64)
+        h_cps, h_off, h_max = dec.device_text(d_tok, d_lens)   # transcripts as UTF-32 on the device
         # sizes the edit kernel's on-chip buffers: one scalar read back (a sync inside the step)
-        max_len = max(ref_max_len, int(d_lens.max().item()))
-        cc, _ = metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps, d_hbeg, d_hend, B, 1, max_len)
-        wc, _ = metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps, d_hbeg, d_hend, B, 2, max_len)
+        max_len = max(ref_max_len, int(h_max.item()))
+        cc, _ = metrics.edit_counts_device(d_rcps, d_roff, h_cps, h_off, B, 1, max_len, dev)
+        wc, _ = metrics.edit_counts_device(d_rcps, d_roff, h_cps, h_off, B, 2, max_len, dev)
         totals = torch.stack([cc.sum(dim=0, dtype=torch.int64), wc.sum(dim=0, dtype=torch.int64)])
         if world > 1:
             dist.all_reduce(totals)
@@ -347,9 +363,10 @@ def run_ours(args, rank, world, local_rank):
             kern_ms.append((e0, e1))
         return totals, d_status
 
-    def step_e2e():
-        """Public API with host inputs: H2D of the logits, decode, D2H, strings, cer/wer."""
-        hyps = dec.decode_batch(None, h_logits, beam_width=args.beam, lengths=h_len)
+    def step_e2e(inp=None, lengths=h_len):
+        """Public API with HOST inputs: the logits reach the GPU inside decode_batch (pinned host
+        memory read in place), transcripts come back as strings, cer()/wer() score them."""
+        hyps = dec.decode_batch(None, h_logits if inp is None else inp, beam_width=args.beam, lengths=lengths)
         if world > 1:
             from coral_b200.sharded import sharded_error_rates
 
@@ -367,7 +384,7 @@ def run_ours(args, rank, world, local_rank):
     parity = None
     if oracle_stats is not None:
         s = oracle_stats["sample"]
-        same = hyps[:s] == oracle_stats["hyps"]
+        same = list(hyps[:s]) == oracle_stats["hyps"]
         from oracle import edit as oracle_edit
 
         same_counts = (metrics.cer(hyps[:s], refs[:s]) == oracle_edit.cer(hyps[:s], refs[:s]) and
@@ -400,13 +417,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
 
-    # ---- timed: end to end through the public API
-    for _ in range(1):
+    # ---- timed: end to end through the public API, ALL --steps
+    for _ in range(2):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         hyps, cer_v, wer_v = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -416,6 +432,68 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+
+    # ---- where an end-to-end step spends its time (separate, untimed-for-the-headline pass with a
+    # synchronisation after every phase; max over ranks)
+    def e2e_phases(n=3):
+        acc = {}
+
+        def mark(name, t_prev):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            acc[name] = acc.get(name, 0.0) + (now - t_prev)
+            return now
+
+        for _ in range(n):
+            barrier()
+            t_ = time.perf_counter()
+            outs = dec.decode_padded(h_logits, h_len, beam_width=args.beam, n_best=1, to_host=False)
+            t_ = mark("decode (launch prep + kernel pulling the pinned host logits)", t_)
+            d_text = dec.device_text(outs[3], outs[4])
+            bad = int(outs[5].abs().max().item())
+            t_ = mark("transcripts -> UTF-32 on the device + status read-back", t_)
+            texts = dec._texts_from_device(*d_text)
+            t_ = mark("D2H of the text + Python strings", t_)
+            metrics._to_device(refs, dev)
+            t_ = mark("references: UTF-32 encode + H2D", t_)
+            if world > 1:
+                from coral_b200.sharded import sharded_error_rates
+
+                sharded_error_rates(texts, refs)
+            else:
+                metrics.cer(texts, refs), metrics.wer(texts, refs)
+            t_ = mark("cer + wer: both edit kernels, one read-back" + (", all-reduce" if world > 1 else ""), t_)
+            assert bad == 0
+        v = torch.tensor([acc[k] / n * 1e3 for k in acc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return {k: round(float(x), 3) for k, x in zip(acc, v.cpu().tolist())}
+
+    phases = e2e_phases()
+
+    # ---- the reference's real call shape: a list of [T_i, V] numpy arrays (what
+    # HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:371 hands to decode_beams_batch),
+    # pageable host memory, packed into the pinned ragged buffer by host threads
+    lst = [wl.logits[u, : wl.lengths[u]] for u in range(B)]
+    for _ in range(2):
+        hy = dec.decode_batch(None, lst, beam_width=args.beam)
+    assert list(hy) == list(hyps)
+    barrier()
+    t0 = time.perf_counter()
+    n_list = max(1, min(args.steps, 5))
+    for _ in range(n_list):
+        hy = dec.decode_batch(None, lst, beam_width=args.beam)
+        if world > 1:
+            from coral_b200.sharded import sharded_error_rates
+
+            sharded_error_rates(hy, refs)
+        else:
+            metrics.cer(hy, refs), metrics.wer(hy, refs)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    list_s = float(t.item())
 
     # ---- work counters (one extra untimed launch with stats)
     st = dec.decode_padded(d_logits, d_len, beam_width=args.beam, n_best=1, collect_stats=True).stats
@@ -438,16 +516,17 @@ def run_ours(args, rank, world, local_rank):
 
         g_ms = timed(lambda: greedy_decode_device(d_logits, d_len, blank_id=45))
         fr = int(wl.lengths.sum())
-        g_bytes = fr * 46 * 4 + 2 * fr * 4  # logits read once; ids written, re-read by the collapse
-        hyp_cps0 = cp_table[dec.decode_launch(d_logits, d_len, None, beam_width=args.beam, n_best=1)[3].view(B, Tm).to(torch.int64)]
-        d_l0 = dec.decode_launch(d_logits, d_len, None, beam_width=args.beam, n_best=1)[4].view(B).to(torch.int64)
-        ml = max(ref_max_len, int(d_l0.max().item()))
-        e_ms = timed(lambda: metrics.edit_counts_spans_device(d_rcps, d_rbeg, d_rend, hyp_cps0, d_hbeg, d_hbeg + d_l0, B, 1, ml))
-        cells = float((torch.from_numpy(np.diff(r_off)).to(dev).double() * d_l0.double()).sum().item())
+        g_bytes = fr * 46 * 4 + fr * 4  # every valid logit read once + the collapsed ids' upper bound
+        o0 = dec.decode_launch(d_logits, d_len, None, beam_width=args.beam, n_best=1)
+        h_cps0, h_off0, h_max0 = dec.device_text(o0[3], o0[4])
+        ml = max(ref_max_len, int(h_max0.item()))
+        e_ms = timed(lambda: metrics.edit_counts_device(d_rcps, d_roff, h_cps0, h_off0, B, 1, ml, dev))
+        hl = (h_off0[1:] - h_off0[:-1]).double()
+        cells = float((torch.from_numpy(np.diff(r_off)).to(dev).double() * hl).sum().item())
         other = {
-            "ctc_argmax_kernel+ctc_collapse_kernel": {
+            "ctc_greedy (argmax + collapse)": {
                 "ms": g_ms, "algorithmic_bytes": g_bytes, "GB_per_s": g_bytes / g_ms / 1e6, "bound": "hbm",
-                "note": "greedy decode of the same logits (configs[0] / config 4 path); inputs 425 MB > L2"},
+                "note": "greedy decode of the same ragged logits (configs[0] / config 4 path); inputs 425 MB > L2"},
             "edit_counts_kernel(chars)": {
                 "ms": e_ms, "cells": cells, "GCUPS": cells / e_ms / 1e6, "bound": "integer ALU / shared memory"},
         }
@@ -456,16 +535,17 @@ def run_ours(args, rank, world, local_rank):
         frames = int(wl.lengths.sum())
         audio = float(synth.audio_seconds(wl.lengths).sum())
         hyp_chars = int(sum(len(h) for h in hyps))
-        # algorithmic bytes of the beam kernel: logits once + LM slots + output
+        # algorithmic bytes of the beam kernel: logits once + LM slots + output.
+        # ONE definition at every N: the oracle's distinct (cache-miss) counts on rank 0's CPU sample.
         alg_logits = frames * 46 * 4
         if oracle_stats is not None:
             s = oracle_stats["sample"]
             scale = B / s
             n_score, probes, n_partial = (oracle_stats[k] * scale for k in ("n_score", "probes", "n_partial"))
-            lm_src = f"oracle cache-miss counts on the {s}-utterance CPU sample, scaled to {B}"
+            lm_src = f"oracle cache-miss counts on rank 0's first {s} utterances, scaled to {B}"
         else:
             n_score, probes, n_partial = float(st[1]), float(st[2]), float(st[4])
-            lm_src = "device counters (no CPU sample in this run)"
+            lm_src = "device counters (--no-cpu-baseline: no oracle sample in this run)"
         alg_lm = probes * 16 + n_score * 16 + n_partial * 8
         alg_out = hyp_chars + 16 * B
         alg_bytes = alg_logits + alg_lm + alg_out
@@ -476,7 +556,7 @@ def run_ours(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         if other:
-            g = other["ctc_argmax_kernel+ctc_collapse_kernel"]
+            g = other["ctc_greedy (argmax + collapse)"]
             g["frac_of_hbm_peak"] = g["GB_per_s"] / peak
         traffic = None
         try:
@@ -484,7 +564,8 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         achieved = alg_bytes / (beam_ms * 1e-3) / 1e9
-        e2e_value = world * B * e2e_steps / e2e_s
+        e2e_value = world * B * args.steps / e2e_s
+        ref_bytes = r_cps.nbytes + r_off.nbytes
         line = {
             "metric": METRIC, "value": world * B * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -493,11 +574,20 @@ def run_ours(args, rank, world, local_rank):
             "config": workload_config(args, B, "value: inputs resident in HBM; e2e: host logits through decode_batch + cer/wer"),
             "audio_s_per_s": world * audio * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(h_logits.numel() * 4 + B * 4 + 2 * (r_cps.nbytes + r_off.nbytes) + 2 * (hyp_chars * 4 + 8 * (B + 1))),
-                    "d2h_bytes_per_step": int(B * Tm + B * (4 + 8 + 8 + 4 + 4) + 2 * B * 20),
-                    "audio_s_per_s": world * audio * e2e_steps / e2e_s, "steps": e2e_steps},
-            "gpu_launches": 3 * args.steps,
-            "kernels_per_step": ["beam_search_kernel", "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
+                    # pinned host logits are pulled by the kernel itself: the valid frames cross PCIe once
+                    "h2d_bytes_per_step": int(frames * 46 * 4 + 2 * B * 4 + ref_bytes),
+                    "d2h_bytes_per_step": int(hyp_chars * 4 + 8 * (B + 1) + 2 * B * 20 + 8),
+                    "audio_s_per_s": world * audio * args.steps / e2e_s, "steps": args.steps,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "input": "pinned padded [B, T_max, V] host tensor + lengths (decode_batch extension)",
+                    "phases_ms": phases,
+                    "list_input": {"value": world * B * n_list / list_s, "unit": UNIT, "steps": n_list,
+                                   "ms_per_step": 1e3 * list_s / n_list,
+                                   "input": "list of B pageable [T_i, V] numpy arrays -> decode_batch(None, list) + cer/wer "
+                                            "(the call shape of HF Wav2Vec2ProcessorWithLM.batch_decode -> decode_beams_batch)"}},
+            "gpu_launches": 6 * args.steps,
+            "kernels_per_step": ["beam_search_kernel", "text_count_kernel", "text_scan_kernel", "text_write_kernel",
+                                 "edit_counts_kernel(chars)", "edit_counts_kernel(words)"],
             "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<128,104,208> (beam widths <= 104; <128,128,320> up to 128)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",

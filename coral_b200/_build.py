@@ -17,13 +17,13 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcoral_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-CU_SOURCES = ["lm.cu", "beam.cu", "greedy.cu", "edit.cu"]
-CC_SOURCES = ["lm_host.cc"]
+CU_SOURCES = ["lm.cu", "beam.cu", "greedy.cu", "edit.cu", "text.cu"]
+CC_SOURCES = ["lm_host.cc", "normalise.cc"]
 HEADERS = ["lm_tables.h", "lm_host.h", "beam_core.h", "handles.h", "common.cuh", os.path.join("..", "..", "include", "coral_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--fmad=false",
+    "-Xcompiler", "-fPIC", "--fmad=false", "-I", OBJ_DIR,
 ]
 
 
@@ -41,10 +41,24 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _unicode_tables() -> str:
+    """CPython's Unicode behaviour as C tables for the text normaliser (csrc/normalise.cc):
+    generated from the running interpreter, so the two cannot drift apart."""
+    gen = os.path.join(CSRC, "gen_unicode_tables.py")
+    out = os.path.join(OBJ_DIR, "unicode_tables.h")
+    if _stale(out, [gen]):
+        import runpy
+
+        runpy.run_path(gen)["main"](out + ".tmp")
+        os.replace(out + ".tmp", out)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
+    _unicode_tables()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
     objs = []

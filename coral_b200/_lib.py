@@ -31,8 +31,15 @@ SIGNATURES = {
     "coral_decoder_free": (_i32, [_vp]),
     "coral_decoder_set_params": (_i32, [_vp, _f64, _f64, _f64, _i32]),
     "coral_decoder_info": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "coral_ctc_beam_decode": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _i32,
+    "coral_ctc_beam_decode": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _i32,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "coral_decoder_tokens_to_text": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "coral_host_pack_rows": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32]),
+    "coral_normaliser_create": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, C.POINTER(_vp)]),
+    "coral_normaliser_free": (_i32, [_vp]),
+    "coral_normaliser_run": (_i32, [_vp, _vp, _vp, _i64, _i32, C.POINTER(_i64)]),
+    "coral_normaliser_fetch": (_i32, [_vp, _vp, _vp, _vp]),
+    "coral_normaliser_unicode_version": (C.c_char_p, []),
     "coral_ctc_greedy": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "coral_ctc_collapse": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "coral_edit_counts": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),

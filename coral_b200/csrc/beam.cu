@@ -19,6 +19,7 @@ struct BeamLaunch {
   const float* logits;
   const int32_t* lengths;
   const int32_t* order;
+  const int64_t* frame_off;  // ragged input: first frame of utterance u in a packed [sum T, V] buffer (or NULL)
   const int32_t* ready;     // streamed input: number of utterances whose logits have landed (or NULL)
   int32_t ready_chunk;      // utterances per host->device chunk
   long long ready_timeout;  // cycles a thread group waits for its chunk before the launch gives up
@@ -60,7 +61,7 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
 // minimum CTAs per SM the register allocation must allow: what shared memory permits
 template <int NT, int BW, int OUTC, bool FRAMES>
 constexpr int min_ctas() {
-  constexpr int by_smem = (int)(232448 / (sizeof(GroupShared<BW, OUTC, FRAMES>) + 1024));
+  constexpr int by_smem = (int)(233472 / (sizeof(GroupShared<BW, OUTC, FRAMES>) + 1024));  // 228 KB per SM, 1 KB reserved per CTA
   constexpr int by_threads = 2048 / NT;
   constexpr int by_regs = 65536 / (NT * 64);  // never ask for fewer than 64 registers per thread
   constexpr int m = by_smem < by_threads ? by_smem : by_threads;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_sea
       }
     }
     UttIO io;
-    io.logits = L.logits + (size_t)u * L.P.T_max * L.P.V;
+    io.logits = L.logits + (L.frame_off ? (size_t)L.frame_off[u] : (size_t)u * L.P.T_max) * L.P.V;
     io.T = L.lengths[u];
     io.out_n = L.out_n + u;
     io.out_logit = L.out_logit + (size_t)u * L.P.n_best;
@@ -337,7 +338,8 @@ int32_t coral_decoder_info(const coral_decoder* d, uint64_t* lexicon_entries, ui
 }
 
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
-                              const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V, int32_t beam_width,
+                              const int32_t* order_dev, const int64_t* frame_offsets_dev, int32_t B, int32_t T_max,
+                              int32_t V, int32_t beam_width,
                               double beam_prune_logp, double token_min_logp, int32_t prune_history,
                               int32_t input_mode, int32_t n_best, int32_t* out_n_beams_dev,
                               double* out_logit_score_dev, double* out_lm_score_dev, uint8_t* out_tokens_dev,
@@ -370,6 +372,20 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.P.n_best = n_best;
   L.P.T_max = T_max > 0 ? T_max : 1;
   L.P.input_mode = input_mode;
+  {
+    // pinned host logits are read in place (zero-copy): plain loads + L2 prefetch of the next
+    // frames (mode 2, default: measured 16.3 ms per 8192 utterances against 15.3 ms for
+    // HBM-resident logits); CORAL_HOST_INPUT_MODE=1 selects uncached loads (46 ms) -- a knob
+    // kept for diagnosing stale-line suspicions, see DESIGN.md
+    cudaPointerAttributes pa;
+    L.P.host_input = 0;
+    if (cudaPointerGetAttributes(&pa, logits_dev) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+      L.P.host_input = 2;
+      if (const char* e = getenv("CORAL_HOST_INPUT_MODE")) { const int v = atoi(e); if (v == 1 || v == 2) L.P.host_input = v; }
+    } else {
+      cudaGetLastError();  // an unregistered host pointer sets a sticky-free error: clear it
+    }
+  }
   L.P.token_min_logp = (float)token_min_logp;
   L.P.beam_prune_logp = beam_prune_logp;
   set_bucket_scale(L.P);
@@ -381,6 +397,7 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.logits = logits_dev;
   L.lengths = lengths_dev;
   L.order = order_dev;
+  L.frame_off = frame_offsets_dev;
   L.B = B;
   L.out_n = out_n_beams_dev;
   L.out_logit = out_logit_score_dev;

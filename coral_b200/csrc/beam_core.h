@@ -44,8 +44,10 @@ inline unsigned long long atom_cas_u64(unsigned long long* p, unsigned long long
   unsigned long long o = *p; if (o == c) *p = v; return o;
 }
 inline uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
+inline uint32_t atom_exch_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 #define CORAL_LANES(NT) for (int lane = 0; lane < (NT); ++lane)
 #define CORAL_GSYNC(NT) ((void)0)
+#define CORAL_WSYNC() ((void)0)
 #else
 #define CORAL_DEV __device__ __forceinline__
 // bulky or rarely executed paths are kept out of line so that the per-frame loop stays
@@ -61,6 +63,7 @@ __device__ __forceinline__ unsigned long long atom_cas_u64(unsigned long long* p
   return atomicCAS(p, c, v);
 }
 __device__ __forceinline__ uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
+__device__ __forceinline__ uint32_t atom_exch_u32(uint32_t* p, uint32_t v) { return atomicExch(p, v); }
 template <int NT>
 __device__ __forceinline__ void group_sync() {
   if (NT == 32) {
@@ -71,6 +74,7 @@ __device__ __forceinline__ void group_sync() {
 }
 #define CORAL_LANES(NT) for (int lane = (int)(threadIdx.x % (NT)), _once = 1; _once; _once = 0)
 #define CORAL_GSYNC(NT) group_sync<NT>()
+#define CORAL_WSYNC() __syncwarp()
 #endif
 
 // ---------------------------------------------------------------- fp64 with fixed rounding
@@ -123,6 +127,7 @@ constexpr int kMaxLabelCps = 8;  // code points per alphabet label
 constexpr uint32_t kNone16 = 0xFFFFu;
 constexpr uint32_t kNoTok = 0xFFu;
 constexpr uint32_t kNoNode = 0xFFFFFFFFu;
+constexpr uint32_t kListEnd = 0xFFFFu;
 
 // beam flags (4 bits in meta)
 constexpr uint32_t kOovPartial = 1u;  // word_part is not a prefix of any unigram-set word
@@ -138,6 +143,7 @@ struct DecodeParams {
   int32_t n_best;       // beams written per utterance (<= beam_width)
   int32_t T_max;        // row pitch of logits [B, T_max, V] and of out_tokens
   int32_t input_mode;   // 0 auto (pyctcdecode's test, evaluated per utterance), 1 logits, 2 probabilities
+  int32_t host_input;   // logits live in pinned HOST memory: 1 = uncached loads, 2 = plain loads + L2 prefetch
   int32_t score_boundary;
   float token_min_logp;  // compared in float32
   double beam_prune_logp;
@@ -249,12 +255,13 @@ struct GroupShared {
   uint32_t o_aux[OUTC];
   uint32_t o_child[OUTC];
   uint32_t o_info[OUTC];
-  // score buckets for ranking (phase 3)
+  // score buckets for ranking (phase 3): per bucket a count and a linked list of its candidates
+  // (built while the candidates are produced), plus the exclusive prefix sums of the counts
   uint32_t bcnt[kNB];
-  uint32_t gcnt[kNB / 8];
-  uint16_t o_pos[OUTC];     // position of a candidate inside its bucket
+  uint32_t bhead[kNB];      // first candidate of the bucket's list (kListEnd = empty)
+  uint16_t bstart[kNB];     // candidates in strictly better buckets (capped at 0xFFFF)
+  uint16_t o_next[OUTC];    // next candidate of the same bucket
   uint8_t o_bkt[OUTC];      // its bucket
-  uint16_t o_sorted[OUTC];  // survivors grouped by bucket (counting sort)
   // staged frames
   float lp[kChunk][kVMax];
   uint8_t kept[kChunk][kVMax];
@@ -500,12 +507,18 @@ struct BeamDecoder {
       const uint32_t inv_v = V > 1 ? 0xFFFFFFFFu / (uint32_t)V + 1u : 0u;
       for (int i = lane; i < nf * V; i += NT) {
         const uint32_t f = V > 1 ? mulhi_u32((uint32_t)i, inv_v) : (uint32_t)i;
+#if defined(__CUDA_ARCH__)
+        // host-resident logits (zero-copy over PCIe): never trust a cached system-memory line
+        sm.lp[f][(uint32_t)i - f * (uint32_t)V] =
+            P.host_input == 1 ? __ldcv(io.logits + (size_t)t0 * V + i) : io.logits[(size_t)t0 * V + i];
+#else
         sm.lp[f][(uint32_t)i - f * (uint32_t)V] = io.logits[(size_t)t0 * V + i];
+#endif
       }
 #if defined(__CUDA_ARCH__)
       // pull the next chunk of this utterance towards L2 while this one is decoded
       const int nxt0 = t0 + kChunk;
-      if (nxt0 < io.T) {
+      if (nxt0 < io.T && P.host_input != 1) {
         const int nn = (io.T - nxt0 < kChunk ? io.T - nxt0 : kChunk) * V;
         const char* base = reinterpret_cast<const char*>(io.logits + (size_t)nxt0 * V);
         for (int off = lane * 128; off < nn * 4; off += NT * 128)
@@ -734,8 +747,7 @@ struct BeamDecoder {
     // counting-sort histogram for phase 3 (over every candidate: the overflow path finds its
     // cut bucket from the same counts)
     const uint32_t b = bucket_of(sm.mhat, scale, comb);
-    const uint32_t pos = atom_add(&sm.bcnt[b], 1u);
-    atom_add(&sm.gcnt[b >> 3], 1u);
+    atom_add(&sm.bcnt[b], 1u);
     if (at < (uint32_t)OUTC) {
       sm.o_key[at] = k;
       sm.o_logit[at] = logit;
@@ -743,8 +755,8 @@ struct BeamDecoder {
       sm.o_aux[at] = aux;
       sm.o_child[at] = child;
       sm.o_info[at] = info;
-      sm.o_pos[at] = (uint16_t)pos;
       sm.o_bkt[at] = (uint8_t)b;
+      sm.o_next[at] = (uint16_t)atom_exch_u32(&sm.bhead[b], at);
     } else if (at < g_cap) {
       g.key[at] = k;
       g.logit[at] = logit;
@@ -768,8 +780,7 @@ struct BeamDecoder {
         // log-prob (+2: merges and word completions can raise a score a little)
         sm.mhat = d_add(d_add(key_to_double(sm.gmax[q ^ 1]), best_lp), 2.0);
       }
-      for (int i = lane; i < kNB; i += NT) sm.bcnt[i] = 0;
-      for (int i = lane; i < kNB / 8; i += NT) sm.gcnt[i] = 0;
+      for (int i = lane; i < kNB; i += NT) { sm.bcnt[i] = 0; sm.bhead[i] = kListEnd; }
       for (uint32_t b = lane; b < nb; b += NT) {
         const uint32_t mt = sm.meta[cur][b];
         bool created;
@@ -1100,51 +1111,67 @@ struct BeamDecoder {
     const uint32_t n = sm.n_out[q];
     const double scale = bucket_scale(P);
     CORAL_LANES(NT) {
-      for (int i = lane; i < kNB; i += NT) sm.bcnt[i] = 0;
-      for (int i = lane; i < kNB / 8; i += NT) sm.gcnt[i] = 0;
+      for (int i = lane; i < kNB; i += NT) { sm.bcnt[i] = 0; sm.bhead[i] = kListEnd; }
     }
     CORAL_GSYNC(NT);
     CORAL_LANES(NT) {
       for (uint32_t i = lane; i < n; i += NT) {
         const uint32_t b = bucket_of(sm.mhat, scale, key_to_double(sm.o_key[i]));
-        sm.o_pos[i] = (uint16_t)atom_add(&sm.bcnt[b], 1u);
+        atom_add(&sm.bcnt[b], 1u);
         sm.o_bkt[i] = (uint8_t)b;
-        atom_add(&sm.gcnt[b >> 3], 1u);
+        sm.o_next[i] = (uint16_t)atom_exch_u32(&sm.bhead[b], i);
       }
     }
     CORAL_GSYNC(NT);
+  }
+  // Exclusive prefix sums of the bucket counts -> bstart. Every warp computes the same 128 values
+  // and stores them (identical stores, so no block barrier is needed: a warp reads only after its
+  // own stores). Host simulation: lane 0 does it sequentially.
+  static CORAL_DEV void scan_buckets(Sm& sm, int lane) {
+#if defined(__CUDA_ARCH__)
+    static_assert(kNB % 32 == 0, "bucket count must be a multiple of the warp size");
+    constexpr int PER = kNB / 32;
+    const int l = lane & 31;
+    uint32_t c[PER];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { c[k] = sm.bcnt[l * PER + k]; s += c[k]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (l >= o) incl += v;
+    }
+    uint32_t run = incl - s;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { sm.bstart[l * PER + k] = (uint16_t)(run > 0xFFFFu ? 0xFFFFu : run); run += c[k]; }
+#else
+    if (lane == 0) {
+      uint32_t run = 0;
+      for (int b = 0; b < kNB; ++b) { sm.bstart[b] = (uint16_t)(run > 0xFFFFu ? 0xFFFFu : run); run += sm.bcnt[b]; }
+    }
+#endif
   }
   static CORAL_DEV void rank_and_commit(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
                                         int cur, int q, unsigned long long thr, bool final_pass,
                                         PhaseTimer* pt = nullptr, int t = 0) {
     const int nxt = cur ^ 1;
     const uint32_t n = sm.n_out[q];
+    CORAL_LANES(NT) { scan_buckets(sm, lane); }
+    CORAL_WSYNC();
+    if (pt) pt->mark(12);
     CORAL_LANES(NT) {
       if (!final_pass) clear_hash(sm, lane);
       for (uint32_t i = lane; i < n; i += NT) {
-        const uint32_t b = sm.o_bkt[i];
-        uint32_t base = 0;
-#pragma unroll 4
-        for (uint32_t g = 0; g < (b >> 3); ++g) base += sm.gcnt[g];
-#pragma unroll 4
-        for (uint32_t d = b & ~7u; d < b; ++d) base += sm.bcnt[d];
-        sm.o_sorted[base + sm.o_pos[i]] = (uint16_t)i;
-        sm.o_pos[i] = (uint16_t)base;  // from here on: first slot of its bucket
-      }
-    }
-    CORAL_GSYNC(NT);
-    if (pt) pt->mark(12);
-    CORAL_LANES(NT) {
-      for (uint32_t i = lane; i < n; i += NT) {
         const unsigned long long ki = sm.o_key[i];
         if (ki < thr) continue;
+        const uint32_t b = sm.o_bkt[i];
+        uint32_t r = sm.bstart[b];
+        // beam_width or more candidates sit in strictly better buckets: it cannot survive the trim
+        if (r >= (uint32_t)P.beam_width) continue;
         const uint32_t oi = sm.o_order[i];
-        const uint32_t base = sm.o_pos[i];
-        const uint32_t cnt = sm.bcnt[sm.o_bkt[i]];
-        uint32_t r = base;
 #pragma unroll 2
-        for (uint32_t m = 0; m < cnt; ++m) {
-          const uint32_t j = sm.o_sorted[base + m];
+        for (uint32_t j = sm.bhead[b]; j != kListEnd; j = sm.o_next[j]) {
           const unsigned long long kj = sm.o_key[j];
           r += kj > ki;
           if (kj == ki) r += sm.o_order[j] < oi;
@@ -1457,8 +1484,8 @@ struct BeamDecoder {
       for (int f = 0; f < nf; ++f) {
         frame_step(sm, lm, P, sc, io, f, cur, q, nb, t0 + f);
         if (sm.status != 0) { failed = true; break; }
-        nb = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
         cur ^= 1;
+        nb = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
         q ^= 1;
       }
     }

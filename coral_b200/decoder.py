@@ -37,8 +37,45 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 MAX_BEAM_WIDTH = 512
-H2D_CHUNK = int(os.environ.get("CORAL_H2D_CHUNK", "512"))  # utterances per host->device chunk (pinned host logits)
+H2D_CHUNK = int(os.environ.get("CORAL_H2D_CHUNK", "512"))  # utterances per host-side packing chunk
 # (large chunks: a launch with few utterances per CTA is dominated by its longest utterances)
+# Host logits: "zerocopy" (default) = the kernel reads pinned host memory in place, valid frames
+# only; "dma" = round 1's chunked cudaMemcpyAsync of the padded batch on a copy stream.
+HOST_INPUT = os.environ.get("CORAL_HOST_INPUT", "zerocopy")
+
+
+def _host_threads() -> int:
+    """Threads for coral_host_pack_rows: this process's share of the cores it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(8, n // max(local, 1)))
+
+
+def _invalidating(name):
+    def method(self, *a, **kw):
+        self._coral_dev = None  # the list no longer holds what was decoded
+        return getattr(list, name)(self, *a, **kw)
+
+    method.__name__ = name
+    return method
+
+
+class DecodedTexts(list):
+    """``list[str]`` of transcripts that also remembers where their UTF-32 code points sit on the
+    device (``_coral_dev`` = (cps int32 tensor, offsets int64 tensor, max_len, token)), so that
+    ``coral_b200.metrics`` can score them without re-encoding and re-uploading the strings. Any
+    in-place mutation drops the device copy; a new list built from it never had one."""
+
+    __slots__ = ("_coral_dev",)
+    _tokens = iter(range(1, 1 << 62))
+
+    for _m in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop",
+               "remove", "sort", "reverse", "clear"):
+        locals()[_m] = _invalidating(_m)
+    del _m
 
 
 def _torch():
@@ -89,6 +126,7 @@ class BeamSearchDecoderCTC:
         # id -> code point table for the fast token->string path (single-code-point labels)
         self._single_cp = all(len(c) <= 1 for c in labels)
         self._cp_table = np.array([ord(c) if len(c) == 1 else 0 for c in labels], dtype=np.uint32)
+        self._latin1 = all(ord(ch) < 256 for c in labels for ch in c)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -194,9 +232,33 @@ class BeamSearchDecoderCTC:
         d_len = lengths.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         d_stats = torch.zeros(32, dtype=torch.int64, device=dev) if collect_stats else None
         B = logits.shape[0]
-        if (logits.device.type == "cpu" and B >= 2 * H2D_CHUNK and logits.dtype == torch.float32
+        if logits.device.type == "cpu" and logits.dtype == torch.float32 and logits.is_contiguous() and \
+                logits.is_pinned() and HOST_INPUT == "zerocopy":
+            # Pinned host logits are read IN PLACE by the kernel (unified addressing makes pinned
+            # memory device-accessible): each valid frame crosses PCIe exactly once, padding rows
+            # never move, and there is no staging copy to wait for.
+            d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+            self._keepalive = (logits,)  # the host buffer must outlive the launch
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self._launch_raw(
+                logits.data_ptr(), B, int(logits.shape[1]), int(logits.shape[2]), dev, d_len, d_order, beam_width,
+                beam_prune_logp, token_min_logp, n_best, input_mode, d_stats, word_frames=word_frames,
+                prune_history=prune_history)
+        elif logits.device.type == "cpu" and HOST_INPUT == "zerocopy" and B > 0:
+            # pageable host logits: the valid rows are packed into a pinned ragged staging buffer
+            # by host threads (chunk by chunk, the kernel already running), then read in place
+            lens_np = np.ascontiguousarray(lengths.cpu().numpy() if torch.is_tensor(lengths) else lengths).astype(np.int64)
+            arr = logits.numpy() if logits.dtype == torch.float32 and logits.is_contiguous() else \
+                np.ascontiguousarray(logits.to(torch.float32).numpy())
+            base = arr.ctypes.data
+            pitch = arr.shape[1] * arr.shape[2] * 4
+            ptrs = base + np.arange(B, dtype=np.int64) * pitch
+            self._keepalive = (arr,)
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self._decode_rows(
+                ptrs, lens_np, int(arr.shape[1]), dev, beam_width, beam_prune_logp, token_min_logp, n_best,
+                input_mode, d_stats, word_frames, prune_history)
+        elif (logits.device.type == "cpu" and B >= 2 * H2D_CHUNK and logits.dtype == torch.float32
                 and logits.is_contiguous() and logits.is_pinned()):
-            # Pinned host logits: ONE launch over the whole batch, fed by a copy stream. The
+            # (CORAL_HOST_INPUT=dma) ONE launch over the whole batch, fed by a copy stream. The
             # copier delivers H2D_CHUNK utterances at a time and bumps a device counter after
             # each chunk; thread groups wait for their utterance's chunk (include/coral_b200.h,
             # ``ready_dev``), so the decode of chunk k overlaps the transfer of chunk k+1.
@@ -222,15 +284,20 @@ class BeamSearchDecoderCTC:
             self._keepalive = (logits, marks)  # host buffers stay alive until the copies ran
             d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self.decode_launch(
                 d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats,
-                ready=(d_ready, H2D_CHUNK), word_frames=word_frames)
+                ready=(d_ready, H2D_CHUNK), word_frames=word_frames, prune_history=prune_history)
         else:
             d_logits = logits.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
             d_order = torch.argsort(d_len, descending=True).to(torch.int32)
             d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = self.decode_launch(
                 d_logits, d_len, d_order, beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats,
-                word_frames=word_frames)
+                word_frames=word_frames, prune_history=prune_history)
         if not to_host:
             return (d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_stats, *wf)
+        return self._to_host((d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf), d_stats)
+
+    @staticmethod
+    def _to_host(outs, d_stats=None) -> DecodedBatch:
+        d_n, d_logit, d_comb, d_tok, d_lens, d_status, *wf = outs
         out = DecodedBatch(d_n.cpu().numpy(), d_logit.cpu().numpy(), d_comb.cpu().numpy(), d_tok.cpu().numpy(),
                            d_lens.cpu().numpy(), d_status.cpu().numpy(),
                            d_stats.cpu().numpy() if d_stats is not None else None,
@@ -243,14 +310,24 @@ class BeamSearchDecoderCTC:
     def decode_launch(self, d_logits, d_len, d_order, beam_width: int = DEFAULT_BEAM_WIDTH,
                       beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
                       n_best: int = 1, input_mode: int = 0, d_stats=None, events=None, ready=None,
-                      word_frames: bool = False):
+                      word_frames: bool = False, prune_history: bool = False):
         """Queue one batched decode on device-resident inputs (asynchronous). ``events`` =
         (start, end) ``torch.cuda.Event`` recorded around the library call on the launching stream.
         ``ready`` = (int32 device counter, chunk) for logits still arriving on another stream."""
+        B, T_max, V = d_logits.shape
+        return self._launch_raw(d_logits.data_ptr(), B, int(T_max), int(V), d_logits.device, d_len, d_order,
+                                beam_width, beam_prune_logp, token_min_logp, n_best, input_mode, d_stats, events,
+                                ready, word_frames, prune_history)
+
+    def _launch_raw(self, logits_ptr: int, B: int, T_max: int, V: int, dev, d_len, d_order,
+                    beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+                    token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, n_best: int = 1, input_mode: int = 0,
+                    d_stats=None, events=None, ready=None, word_frames: bool = False, prune_history: bool = False,
+                    d_frame_off=None):
+        """``logits_ptr``: device memory, or pinned host memory (read in place). ``d_frame_off``:
+        int64 [B] first frame of each utterance in a packed ``[sum T, V]`` buffer (ragged input)."""
         torch = _torch()
         h = self._handle()
-        dev = d_logits.device
-        B, T_max, V = d_logits.shape
         Tm = max(int(T_max), 1)
         d_n = torch.empty(B, dtype=torch.int32, device=dev)
         d_logit = torch.empty((B, n_best), dtype=torch.float64, device=dev)
@@ -266,11 +343,13 @@ class BeamSearchDecoderCTC:
         if events is not None:
             events[0].record()
         _lib.check(_lib.load().coral_ctc_beam_decode(
-            h, d_logits.data_ptr(), d_len.data_ptr(), d_order.data_ptr() if d_order is not None else None, B,
-            int(T_max), V, int(beam_width), float(beam_prune_logp), float(token_min_logp), 0, int(input_mode),
+            h, logits_ptr, d_len.data_ptr(), d_order.data_ptr() if d_order is not None else None,
+            d_frame_off.data_ptr() if d_frame_off is not None else None, B,
+            int(T_max), V, int(beam_width), float(beam_prune_logp), float(token_min_logp), int(bool(prune_history)),
+            int(input_mode),
             int(n_best), d_n.data_ptr(), d_logit.data_ptr(), d_comb.data_ptr(), d_tok.data_ptr(), d_lens.data_ptr(),
             d_status.data_ptr(), d_stats.data_ptr() if d_stats is not None else None,
-            ready[0].data_ptr() if ready is not None else None, int(ready[1]) if ready is not None else 0,
+            _lib.ptr(ready[0]) if ready is not None else None, int(ready[1]) if ready is not None else 0,
             d_wf.data_ptr() if word_frames else None, d_wn.data_ptr() if word_frames else None, max_words,
             _lib.stream_ptr(dev)))
         if events is not None:
@@ -279,30 +358,116 @@ class BeamSearchDecoderCTC:
             return d_n, d_logit, d_comb, d_tok, d_lens, d_status, d_wf, d_wn
         return d_n, d_logit, d_comb, d_tok, d_lens, d_status
 
-    def device_tokens_to_text(self, d_tok, d_lens) -> list[str]:
-        """Winning token rows still on the device ``[B, T]`` uint8 + lengths ``[B]`` -> strings:
-        the alphabet lookup and the compaction run on the GPU, one flat code-point buffer comes
-        back, and the host only decodes UTF-32 and slices."""
+    # ------------------------------------------------------------ host rows -> ragged pinned buffer
+    def _staging(self, n_floats: int):
+        """Pinned staging buffer (grown geometrically, reused call after call). A launch that may
+        still be reading it is waited for before it is overwritten."""
         torch = _torch()
-        B, T = d_tok.shape
+        ev = getattr(self, "_staging_event", None)
+        if ev is not None:
+            ev.synchronize()
+            self._staging_event = None
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < n_floats:
+            self._pinned = buf = torch.empty(max(n_floats, 1 << 16) * 5 // 4, dtype=torch.float32, pin_memory=True)
+        return buf
+
+    def _decode_rows(self, ptrs, lens_np, T_pitch, dev, beam_width, beam_prune_logp, token_min_logp, n_best,
+                     input_mode, d_stats, word_frames, prune_history):
+        """Decode utterances given as host row pointers (``ptrs`` int64 [B] addresses of ``[T_i, V]``
+        float32 C-contiguous blocks, ``lens_np`` int64 [B] frames). The rows are packed into the
+        pinned ragged staging buffer by host threads and read from there by the kernel (zero-copy).
+        Large batches are packed ``H2D_CHUNK`` utterances at a time while the kernel already runs:
+        a pinned host counter tells the thread groups which chunks have landed."""
+        torch = _torch()
+        lib = _lib.load()
+        B = len(lens_np)
+        V = len(self._idx2vocab)
+        row_bytes = V * 4
+        off = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens_np, out=off[1:])
+        stage = self._staging(int(off[-1]) * V)
+        dst_off = off[:-1] * row_bytes
+        nbytes = lens_np * row_bytes
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
+        d_len = torch.from_numpy(lens_np.astype(np.int32)).to(dev, non_blocking=True)
+        d_foff = torch.from_numpy(off[:-1].copy()).to(dev, non_blocking=True)
+        nthr = _host_threads()
+        n_chunks = (B + H2D_CHUNK - 1) // H2D_CHUNK
+        Tm = max(int(T_pitch), int(lens_np.max()) if B else 0, 1)
+        if n_chunks < 2:
+            _lib.check(lib.coral_host_pack_rows(ptrs.ctypes.data, nbytes.ctypes.data, dst_off.ctypes.data, B,
+                                                stage.data_ptr(), nthr))
+            d_order = torch.argsort(d_len, descending=True).to(torch.int32)
+            out = self._launch_raw(stage.data_ptr(), B, Tm, V, dev, d_len, d_order, beam_width, beam_prune_logp,
+                                   token_min_logp, n_best, input_mode, d_stats, word_frames=word_frames,
+                                   prune_history=prune_history, d_frame_off=d_foff)
+        else:
+            if getattr(self, "_ready_host", None) is None:
+                self._ready_host = torch.zeros(16, dtype=torch.int32).pin_memory()
+            ready = self._ready_host
+            ready_np = ready.numpy()
+            ready_np[0] = 0
+            chunk_id = np.arange(B, dtype=np.int64) // H2D_CHUNK
+            order = np.argsort(chunk_id * (Tm + 1) - lens_np, kind="stable").astype(np.int32)
+            d_order = torch.from_numpy(order).to(dev, non_blocking=True)
+            # chunk 0 is packed before the launch: nobody starts by waiting
+            a0, b0 = 0, min(B, H2D_CHUNK)
+            _lib.check(lib.coral_host_pack_rows(ptrs[a0:].ctypes.data, nbytes[a0:].ctypes.data,
+                                                dst_off[a0:].ctypes.data, b0 - a0, stage.data_ptr(), nthr))
+            ready_np[0] = b0
+            out = self._launch_raw(stage.data_ptr(), B, Tm, V, dev, d_len, d_order, beam_width, beam_prune_logp,
+                                   token_min_logp, n_best, input_mode, d_stats, ready=(ready, H2D_CHUNK),
+                                   word_frames=word_frames, prune_history=prune_history, d_frame_off=d_foff)
+            for k in range(1, n_chunks):
+                a0, b0 = k * H2D_CHUNK, min(B, (k + 1) * H2D_CHUNK)
+                _lib.check(lib.coral_host_pack_rows(ptrs[a0:].ctypes.data, nbytes[a0:].ctypes.data,
+                                                    dst_off[a0:].ctypes.data, b0 - a0, stage.data_ptr(), nthr))
+                ready_np[0] = b0  # x86 keeps stores in order: the rows are visible before the counter
+        self._staging_event = torch.cuda.Event()
+        self._staging_event.record(torch.cuda.current_stream(dev))
+        return out
+
+    def device_text(self, d_tok, d_lens):
+        """Winning token rows on the device (``d_tok`` uint8 ``[B, n_best, T]`` + ``d_lens`` int32
+        ``[B, n_best]``) -> (code points int32 ``[cap]``, offsets int64 ``[B + 1]``, max_len int32
+        scalar), all device tensors: the best beam's text as flat UTF-32 (``coral_decoder_tokens_to_text``)."""
+        torch = _torch()
+        B, nb, T = d_tok.shape
         dev = d_tok.device
-        if getattr(self, "_d_cp_table", None) is None or self._d_cp_table.device != dev:
-            self._d_cp_table = torch.from_numpy(self._cp_table.astype(np.int64)).to(dev).to(torch.int32)
-        lens = d_lens.to(torch.int64)
-        mask = torch.arange(T, device=dev)[None, :] < lens[:, None]
-        flat = self._d_cp_table[d_tok[mask].to(torch.int64)]
-        # labels longer than one code point (CoRal's "<s>" / "</s>") have no table entry; they
-        # practically never win, so one scalar tells whether the host path is needed at all
-        if not self._single_cp and bool((flat == 0).any().item()):
-            return self.tokens_to_text(d_tok.cpu().numpy(), d_lens.cpu().numpy())
-        off = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(lens, 0, out=off[1:])
-        text = flat.cpu().numpy().view(np.uint32).tobytes().decode("utf-32-le")
-        o = off.cpu().tolist()
-        return [text[a:b] for a, b in zip(o[:-1], o[1:])]
+        maxcp = max([len(c) for c in self._alphabet.labels] + [1])
+        cap = max(1, B * T * maxcp)
+        d_cps = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        d_work = torch.empty(max(B, 1), dtype=torch.int64, device=dev)
+        d_max = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().coral_decoder_tokens_to_text(
+            self._handle(), d_tok.data_ptr(), nb * T, d_lens.data_ptr(), nb, B, d_cps.data_ptr(), cap,
+            d_off.data_ptr(), d_work.data_ptr(), d_max.data_ptr(), _lib.stream_ptr(dev)))
+        return d_cps, d_off, d_max
+
+    def device_tokens_to_text(self, d_tok, d_lens) -> list[str]:
+        """``[B, T]`` uint8 token rows + ``[B]`` lengths on the device -> Python strings (the text is
+        assembled on the GPU; the host decodes one flat UTF-32 buffer and slices it)."""
+        return self._texts_from_device(*self.device_text(d_tok[:, None, :], d_lens[:, None]))
+
+    def _texts_from_device(self, d_cps, d_off, d_max) -> "DecodedTexts":
+        B = d_off.numel() - 1
+        off = d_off.cpu()                                 # sync #1: offsets (and thereby the total)
+        o = off.tolist()
+        total = o[-1]
+        cps = d_cps[:total].cpu().numpy()                 # sync #2: exactly the code points
+        if self._latin1:  # every label is below U+0100 (CoRal's alphabet): one byte per symbol decodes faster
+            text = cps.astype(np.uint8).tobytes().decode("latin-1")
+        else:
+            text = cps.view(np.uint32).tobytes().decode("utf-32-le", "surrogatepass")
+        out = DecodedTexts(text[a:b] for a, b in zip(o[:-1], o[1:]))
+        max_len = int(d_max.item()) if B else 0
+        out._coral_dev = (d_cps[:total], d_off, max_len, ("decoded", next(DecodedTexts._tokens)))
+        return out
 
     def tokens_to_text(self, tokens: np.ndarray, lens: np.ndarray) -> list[str]:
-        """Alphabet indices -> strings for ``[N, T]`` token rows with ``[N]`` lengths."""
+        """Alphabet indices -> strings for ``[N, T]`` token rows with ``[N]`` lengths (host arrays)."""
         N, T = tokens.shape
         lens = lens.astype(np.int64)
         mask = np.arange(T)[None, :] < lens[:, None]
@@ -316,23 +481,21 @@ class BeamSearchDecoderCTC:
         labels = self._alphabet.labels
         return ["".join(labels[t] for t in flat[off[i] : off[i + 1]]) for i in range(N)]
 
-    def _pad(self, logits_list):
-        """list of [T_i, V] arrays -> (pinned padded [B, T_max, V] tensor, lengths)."""
-        torch = _torch()
-        for lg in logits_list:
-            self._check_logits_dimension(lg)
-        B = len(logits_list)
+    def _rows(self, logits_list):
+        """list of ``[T_i, V]`` arrays -> (row pointers int64 [B], frames int64 [B], keep-alive list)."""
         V = len(self._idx2vocab)
-        lengths = np.fromiter((lg.shape[0] for lg in logits_list), dtype=np.int32, count=B)
-        T_max = int(lengths.max()) if B else 0
-        need = B * max(T_max, 1) * V
-        if getattr(self, "_pinned", None) is None or self._pinned.numel() < need:
-            self._pinned = torch.empty(need, dtype=torch.float32, pin_memory=True)
-        buf = self._pinned[:need].view(B, max(T_max, 1), V)
-        nb = buf.numpy()
-        for i, lg in enumerate(logits_list):
-            nb[i, : lengths[i]] = lg
-        return buf, lengths
+        keep = []
+        for lg in logits_list:
+            if not isinstance(lg, np.ndarray):
+                lg = np.asarray(lg)
+            self._check_logits_dimension(lg)
+            if lg.dtype != np.float32 or not lg.flags.c_contiguous:
+                lg = np.ascontiguousarray(lg, dtype=np.float32)
+            keep.append(lg)
+        B = len(keep)
+        ptrs = np.fromiter((a.ctypes.data for a in keep), dtype=np.int64, count=B)
+        lens = np.fromiter((a.shape[0] for a in keep), dtype=np.int64, count=B)
+        return ptrs, lens, keep
 
     # ---------------------------------------------------- pyctcdecode's public API
     def decode_beams(self, logits, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
@@ -349,18 +512,27 @@ class BeamSearchDecoderCTC:
             raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
         if lm_start_state is not None:
             raise NotImplementedError("lm_start_state (stateful decoding) is not implemented")
-        logits_list = [np.asarray(lg) for lg in logits_list]
+        logits_list = list(logits_list)
         if not logits_list:
             return []
-        buf, lengths = self._pad(logits_list)
+        if prune_history:
+            raise NotImplementedError("prune_history=True is not implemented yet (SURVEY.md section 8f N4)")
+        if not 1 <= beam_width <= MAX_BEAM_WIDTH:
+            raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
+        torch = _torch()
+        self._handle()
+        dev = torch.device("cuda", self._device)
+        ptrs, lens, keep = self._rows(logits_list)
         n_best = max(1, min(int(n_best), int(beam_width)))
+        T_max = max(int(lens.max()), 1)
         # bound the word-frame output buffer (B x n_best x max_words x 8 bytes) per launch
-        per_utt = n_best * ((buf.shape[1] + 1) // 2 + 1) * 8 + n_best * buf.shape[1]
+        per_utt = n_best * ((T_max + 1) // 2 + 1) * 8 + n_best * T_max
         step = max(1, min(len(logits_list), (1 << 30) // max(per_utt, 1)))
         res = []
         for a0 in range(0, len(logits_list), step):
-            out = self.decode_padded(buf[a0:a0 + step], lengths[a0:a0 + step], beam_width, beam_prune_logp,
-                                     token_min_logp, prune_history, n_best=n_best, word_frames=True)
+            outs = self._decode_rows(ptrs[a0:a0 + step], lens[a0:a0 + step], 0, dev, beam_width, beam_prune_logp,
+                                     token_min_logp, n_best, 0, None, True, prune_history)
+            out = self._to_host(outs)
             B, nb = out.lens.shape
             texts = self.tokens_to_text(out.tokens.reshape(B * nb, -1), out.lens.reshape(-1))
             for u in range(B):
@@ -373,11 +545,14 @@ class BeamSearchDecoderCTC:
                     ls, cs = float(out.logit_score[u, r]), float(out.lm_score[u, r])
                     beams.append((text, frames, ls, cs) if mp_safe else (text, None, frames, ls, cs))
                 res.append(beams)
+        del keep
         return res
 
     def decode(self, logits, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
                token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, hotwords=None,
                hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, lm_start_state=None) -> str:
+        if lm_start_state is not None:
+            raise NotImplementedError("lm_start_state (stateful decoding) is not implemented")
         return self.decode_batch(None, [logits], beam_width, beam_prune_logp, token_min_logp, hotwords,
                                  hotword_weight)[0]
 
@@ -398,19 +573,30 @@ class BeamSearchDecoderCTC:
         arrays, or (extension) a padded ``[B, T_max, V]`` array/tensor with ``lengths``."""
         if hotwords:
             raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
+        torch = _torch()
         if lengths is None:
-            logits_list = [np.asarray(lg) for lg in logits_list]
+            logits_list = list(logits_list)
             if not logits_list:
                 return []
-            logits_list, lengths = self._pad(logits_list)
-        d_n, d_logit, d_comb, d_tok, d_lens, d_status, _ = self.decode_padded(
-            logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1, to_host=False)
-        texts = self.device_tokens_to_text(d_tok[:, 0, :], d_lens[:, 0])
-        status = d_status.cpu().numpy()
-        if status.any():
+            if not 1 <= beam_width <= MAX_BEAM_WIDTH:
+                raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
+            self._handle()
+            dev = torch.device("cuda", self._device)
+            ptrs, lens, keep = self._rows(logits_list)
+            outs = self._decode_rows(ptrs, lens, 0, dev, beam_width, beam_prune_logp, token_min_logp, 1, 0, None,
+                                     False, False)
+            d_tok, d_lens, d_status = outs[3], outs[4], outs[5]
+        else:
+            d_n, d_logit, d_comb, d_tok, d_lens, d_status, _ = self.decode_padded(
+                logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1, to_host=False)
+        d_text = self.device_text(d_tok, d_lens)
+        # one small read-back tells whether any utterance ran out of arena capacity
+        bad_any = int(d_status.abs().max().item()) if d_status.numel() else 0
+        if bad_any:
+            status = d_status.cpu().numpy()
             bad = np.nonzero(status)[0]
             raise _lib.CoralError(int(status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
-        return texts
+        return self._texts_from_device(*d_text)
 
     # ------------------------------------------------------------- serialisation
     def save_to_dir(self, filepath: str) -> None:

@@ -60,11 +60,10 @@ def score_records(df: pd.DataFrame, categories: list[str], char_counts: np.ndarr
 
 def get_score_df(df: pd.DataFrame, categories: list[str]) -> pd.DataFrame:
     """``df`` needs the category columns plus ``prediction`` and ``text`` (the label)."""
-    from . import metrics as _m
+    from .metrics import _pair_counts
 
     preds = df.prediction.tolist()
     labs = df.text.tolist()
-    _m._UPLOAD_CACHE.clear()
-    char_counts = edit_counts(preds, labs, "chars")
-    word_counts = edit_counts(preds, labs, "words")
+    both = _pair_counts(preds, labs, ("chars", "words"))  # aligned once; the groups only sum integers
+    char_counts, word_counts = both["chars"], both["words"]
     return pd.DataFrame.from_records(data=score_records(df, categories, char_counts, word_counts))

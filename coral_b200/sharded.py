@@ -69,12 +69,12 @@ def rates_from_totals(totals: np.ndarray, normalise: bool = True):
 
 def sharded_error_rates(predictions, labels, normalise: bool = True, process_group=None) -> dict:
     """CER / WER over the union of all ranks' (prediction, label) shards."""
-    from .metrics import edit_counts
+    from .metrics import _as_lists, _pair_counts
 
-    predictions = list(predictions)
-    labels = list(labels)
-    cc = edit_counts(predictions, labels, "chars")
-    wc = edit_counts(predictions, labels, "words")
+    predictions, labels = _as_lists(predictions if isinstance(predictions, list) else list(predictions),
+                                    labels if isinstance(labels, list) else list(labels))
+    both = _pair_counts(predictions, labels, ("chars", "words"))
+    cc, wc = both["chars"], both["words"]
     totals = reduce_counts(cc, wc, process_group=process_group)
     cers, wers = rates_from_totals(totals, normalise)
     return dict(cer=cers[0], wer=wers[0], totals=totals)

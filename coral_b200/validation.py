@@ -30,13 +30,12 @@ class ValidationScores:
 
 
 def validation_scores(predictions, labels, max_cer: float = 0.6, normalise: bool = True) -> ValidationScores:
-    from . import metrics as _m
+    from .metrics import _as_lists, _pair_counts
 
-    predictions = list(predictions)
-    labels = list(labels)
-    _m._UPLOAD_CACHE.clear()
-    cc = edit_counts(predictions, labels, "chars")
-    wc = edit_counts(predictions, labels, "words")
+    predictions, labels = _as_lists(predictions if isinstance(predictions, list) else list(predictions),
+                                    labels if isinstance(labels, list) else list(labels))
+    both = _pair_counts(predictions, labels, ("chars", "words"))  # one marshalling, both kernels, one read-back
+    cc, wc = both["chars"], both["words"]
     asr_cer = per_sample_rates(cc, normalise)
     asr_wer = per_sample_rates(wc, normalise)
     return ValidationScores(

@@ -29,6 +29,7 @@ extern "C" {
 
 typedef struct coral_lm coral_lm;
 typedef struct coral_decoder coral_decoder;
+typedef struct coral_normaliser coral_normaliser;
 
 #define CORAL_OK 0
 #define CORAL_EARG (-1)
@@ -94,6 +95,13 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *   logits_dev   float32 [B, T_max, V]; rows >= lengths[b] are ignored
  *   lengths_dev  int32 [B]
  *   order_dev    int32 [B] processing order (longest first balances the tail) or NULL
+ *   frame_offsets_dev  int64 [B] or NULL. Ragged input: logits_dev is a packed [sum T, V] buffer
+ *                and utterance b starts at frame frame_offsets_dev[b] (what the list of [T_i, V]
+ *                arrays of HF:...processing_wav2vec2_with_lm.py:371 becomes without moving any
+ *                padding). T_max is then only the pitch of out_tokens (>= max lengths).
+ *                logits_dev may also be PINNED HOST memory (cudaHostAlloc / torch pin_memory:
+ *                device-accessible under unified addressing): the kernel then pulls each valid
+ *                frame over PCIe exactly once, with no staging copy -- the end-to-end path.
  *   input_mode   0 = pyctcdecode's auto-detection of probabilities vs logits (per utterance,
  *                inside the kernel), 1 logits, 2 probs
  *   n_best       beams returned per utterance (<= beam_width)
@@ -126,14 +134,38 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *                   holds every possible transcript. NULL selects the kernel without word timing.
  * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
-                              const int32_t* order_dev, int32_t B, int32_t T_max, int32_t V,
-                              int32_t beam_width, double beam_prune_logp, double token_min_logp,
+                              const int32_t* order_dev, const int64_t* frame_offsets_dev, int32_t B,
+                              int32_t T_max, int32_t V, int32_t beam_width, double beam_prune_logp, double token_min_logp,
                               int32_t prune_history, int32_t input_mode, int32_t n_best,
                               int32_t* out_n_beams_dev, double* out_logit_score_dev, double* out_lm_score_dev,
                               uint8_t* out_tokens_dev, int32_t* out_lens_dev, int32_t* out_status_dev,
                               uint64_t* stats_dev, const int32_t* ready_dev, int32_t ready_chunk,
                               int32_t* out_word_frames_dev, int32_t* out_word_counts_dev, int32_t max_words,
                               void* stream);
+
+/* The text of returned beams as UTF-32 ON THE DEVICE: what pyctcdecode builds with
+ * "".join(labels[t] ...) for the beam it returns (UP:pyctcdecode decoder.py), kept where the
+ * metric kernels can read it (R:src/coral/metrics.py:8-61 -> coral_edit_counts) so that the
+ * hypotheses never make the strings -> UTF-32 -> host-to-device round trip.
+ *   tokens_dev   uint8 rows of alphabet indices; row b starts at tokens_dev + b * row_pitch
+ *                (beam 0 of out_tokens [B, n_best, T_max]: row_pitch = n_best * T_max)
+ *   lens_dev     int32, length of row b at lens_dev[b * lens_stride]
+ *   out_cps_dev  uint32 [cps_cap] flat code points (cps_cap >= sum of lengths x longest label)
+ *   out_offsets_dev int64 [B + 1]
+ *   work_dev     int64 [B] scratch
+ *   out_max_len_dev int32 scalar or NULL: longest transcript in code points */
+int32_t coral_decoder_tokens_to_text(const coral_decoder* dec, const uint8_t* tokens_dev, int64_t row_pitch,
+                                     const int32_t* lens_dev, int64_t lens_stride, int32_t B,
+                                     uint32_t* out_cps_dev, int64_t cps_cap, int64_t* out_offsets_dev,
+                                     int64_t* work_dev, int32_t* out_max_len_dev, void* stream);
+
+/* HOST helper: copies n byte ranges src[i][0 .. n_bytes[i]) to dst + dst_offsets[i] with
+ * n_threads host threads. Packs the list of [T_i, V] float32 arrays that
+ * Wav2Vec2ProcessorWithLM.batch_decode hands to decode_beams_batch
+ * (HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:371, :398-406) into one pinned ragged
+ * buffer for coral_ctc_beam_decode(frame_offsets_dev). Pure host code, no CUDA call. */
+int32_t coral_host_pack_rows(const void* const* src, const int64_t* n_bytes, const int64_t* dst_offsets,
+                             int64_t n, void* dst, int32_t n_threads);
 
 /* -------------------------------------------------------------------- greedy (A3/A4) */
 
@@ -177,6 +209,32 @@ int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_
                                 const int64_t* hyp_begin_dev, const int64_t* hyp_end_dev, int64_t n_pairs,
                                 int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,
                                 int32_t* out_status_dev, void* stream);
+
+/* --------------------------------------------------------- text normaliser */
+
+/* HOST code. The text part of coral.data.process_example (R:src/coral/data.py:658-701) as called
+ * between decoding and scoring with audio_column=None (R:src/coral/evaluate.py:61-72,
+ * R:src/coral/validation.py:121-132), incl. coral.utils.convert_numeral_to_words
+ * (R:src/coral/utils.py:303-472): numerals -> words, lower, filler words, NFKC, conversion dict (in
+ * order), characters_to_keep (case-insensitive), space collapsing, line stripping.
+ *   keep_cps / n_keep      characters_to_keep as code points; n_keep < 0 means None (keep all)
+ *   conv_cps, conv_offsets conversion_dict.items() in order: key0, value0, key1, value1, ... as one
+ *                          UTF-32 buffer with 2 * n_conv + 1 offsets */
+int32_t coral_normaliser_create(const uint32_t* keep_cps, int64_t n_keep, const uint32_t* conv_cps,
+                                const int64_t* conv_offsets, int64_t n_conv, int32_t lower_case,
+                                int32_t convert_numerals, coral_normaliser** out);
+int32_t coral_normaliser_free(coral_normaliser* h);
+/* Normalises n strings (UTF-32 + offsets [n + 1]) with n_threads host threads; the results stay in
+ * the handle. out_total = code points of the results. */
+int32_t coral_normaliser_run(coral_normaliser* h, const uint32_t* cps, const int64_t* offsets, int64_t n,
+                             int32_t n_threads, int64_t* out_total);
+/* Copies the results of the last run: out_cps [total], out_offsets [n + 1], out_status [n]
+ * (0 = normalised; 1 = holds something this restatement refuses instead of approximating: a Greek
+ * capital sigma under lower_case, a non-ASCII decimal digit under convert_numerals). */
+int32_t coral_normaliser_fetch(const coral_normaliser* h, uint32_t* out_cps, int64_t* out_offsets,
+                               int32_t* out_status);
+/* Unicode version of the tables compiled in (from the interpreter that ran the build). */
+const char* coral_normaliser_unicode_version(void);
 
 #ifdef __cplusplus
 }

@@ -66,7 +66,7 @@ def test_argument_errors_map_to_the_reference_exceptions():
     with pytest.raises(ValueError):
         _lib.check(lib.coral_edit_counts(None, None, None, None, 4, 1, 10, 0, None, None, None))
     with pytest.raises(ValueError):  # beam_width out of range is rejected before any CUDA call
-        _lib.check(lib.coral_ctc_beam_decode(None, None, None, None, 1, 1, 46, 100, -10.0, -5.0, 0, 0, 1,
+        _lib.check(lib.coral_ctc_beam_decode(None, None, None, None, None, 1, 1, 46, 100, -10.0, -5.0, 0, 0, 1,
                                              None, None, None, None, None, None, None, None, 0, None, None, 0, None))
 
 

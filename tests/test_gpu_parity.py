@@ -441,6 +441,51 @@ def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, 
         beams_equal(oracle_decoder.decode_beams(x), g)
 
 
+def test_host_inputs_are_read_in_place_and_packed_ragged(gpu_decoder, torch_cuda, cache_dir, rng):
+    """Host logits never get a staging copy on the device: a pinned padded tensor is read in place
+    by the kernel, pageable arrays (a padded array, or the list of [T_i, V] arrays HF hands over)
+    are packed into ONE pinned ragged buffer chunk by chunk while the kernel runs. Different
+    batches alternate through the same staging buffer (a stale cached line of the previous batch
+    would show), the transcripts carry their device-resident text into cer()/wer(), and all of it
+    equals the device-resident launch."""
+    import synth
+    from coral_b200 import decoder as dmod, metrics
+    from oracle import edit as oe
+
+    torch = torch_cuda
+    w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
+    n = 2 * dmod.H2D_CHUNK + 91
+    batches = []
+    for _ in range(2):
+        idx = np.concatenate([rng.permutation(256) for _ in range(6)])[:n]
+        want = gpu_decoder.decode_padded(torch.from_numpy(w.logits[idx]).cuda(), w.lengths[idx], n_best=1)
+        texts = gpu_decoder.tokens_to_text(want.tokens[:, 0, :], want.lens[:, 0])
+        batches.append((idx, want, texts))
+    for rep in range(3):
+        for idx, want, texts in batches:
+            lst = [w.logits[u, : w.lengths[u]] for u in idx]           # pageable, ragged
+            got = gpu_decoder.decode_batch(None, lst)
+            assert list(got) == texts
+            refs = [w.references[u] for u in idx]
+            assert getattr(got, "_coral_dev", None) is not None       # text stayed on the device
+            assert metrics.cer(got, refs) == oe.cer(texts, refs) and metrics.wer(got, refs) == oe.wer(texts, refs)
+            if rep == 0:
+                pinned = torch.from_numpy(w.logits[idx]).pin_memory()  # pinned, padded: zero-copy
+                a = gpu_decoder.decode_padded(pinned, w.lengths[idx], n_best=1)
+                b = gpu_decoder.decode_padded(w.logits[idx], w.lengths[idx], n_best=1)  # pageable, padded
+                for k in ("n_beams", "tokens", "lens", "logit_score", "lm_score"):
+                    assert np.array_equal(getattr(a, k), getattr(want, k)), k
+                    assert np.array_equal(getattr(b, k), getattr(want, k)), k
+    # a mutated transcript list must not be scored from the stale device copy
+    got = gpu_decoder.decode_batch(None, [w.logits[u, : w.lengths[u]] for u in range(8)])
+    refs = [w.references[u] for u in range(8)]
+    got[0] = got[0] + " x"
+    assert metrics.cer(got, refs) == oe.cer(list(got), refs)
+    # small batches (no chunking) and a mixed-dtype / non-contiguous list
+    odd = [np.asfortranarray(w.logits[0, : w.lengths[0]]), w.logits[1, : w.lengths[1]].astype(np.float64)]
+    assert list(gpu_decoder.decode_batch(None, odd)) == list(gpu_decoder.decode_batch(None, [w.logits[0, : w.lengths[0]], w.logits[1, : w.lengths[1]]]))
+
+
 def test_stalled_input_stream_fails_the_launch_instead_of_hanging(gpu_decoder, torch_cuda, small_workload, monkeypatch):
     """A ready counter that never moves (a copier that died) must end the launch with an error
     status for every utterance after ONE timeout, not hang the device."""

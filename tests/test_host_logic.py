@@ -170,3 +170,25 @@ def test_group_masks_enumeration_matches_reference_rules():
     # single-valued category: every non-None choice "filters nothing" and is skipped (:187-192)
     df2 = df.assign(gender="f")
     assert all(c[1] is None for c, _ in group_masks(df2, cats))
+
+
+def test_host_pack_rows_packs_ragged_rows_with_threads():
+    """coral_host_pack_rows (pure host code): the list of [T_i, V] arrays becomes one ragged buffer."""
+    from coral_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for n_threads in (1, 4):
+        rows = [rng.standard_normal((int(rng.integers(0, 700)), 46)).astype(np.float32) for _ in range(300)]
+        lens = np.array([r.shape[0] for r in rows], dtype=np.int64)
+        off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        ptrs = np.array([r.ctypes.data for r in rows], dtype=np.int64)
+        nbytes = lens * 46 * 4
+        dst_off = off[:-1] * 46 * 4
+        dst = np.full((int(off[-1]), 46), np.nan, dtype=np.float32)
+        _lib.check(lib.coral_host_pack_rows(ptrs.ctypes.data, nbytes.ctypes.data, dst_off.ctypes.data, len(rows),
+                                            dst.ctypes.data, n_threads))
+        assert np.array_equal(dst, np.concatenate(rows, axis=0))
+    with pytest.raises(ValueError):
+        _lib.check(lib.coral_host_pack_rows(None, None, None, 3, None, 1))
