@@ -36,14 +36,14 @@ struct BeamLaunch {
   unsigned long long* stats;
   uint8_t* scratch;
   unsigned long long slot_bytes;
-  uint32_t node_cap, bnd_cap, ch_size, outs_cap, wf_cap;
+  uint32_t node_cap, bnd_cap, ch_size, outs_cap, wf_cap, hist_cap;
   int32_t* work;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_cap, uint32_t ch_size,
-                                              uint32_t outs_cap, uint32_t wf_cap, size_t off[7]) {
+                                              uint32_t outs_cap, uint32_t wf_cap, uint32_t hist_cap, size_t off[8]) {
   size_t o = 0;
   off[0] = o; o = align16(o + (size_t)node_cap * 4);       // node_parent
   off[1] = o; o = align16(o + (size_t)node_cap * 4);       // node_info
@@ -52,6 +52,7 @@ __host__ __device__ inline size_t slot_layout(uint32_t node_cap, uint32_t bnd_ca
   off[4] = o; o = align16(o + (size_t)bnd_cap * sizeof(BndRec));
   off[5] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: key, logit
   off[6] = o; o = align16(o + (size_t)outs_cap * 16);      // overflow candidates: order, aux, child, info
+  off[7] = o; o = align16(o + (size_t)hist_cap * sizeof(HistRec));  // prune_history records (0 when off)
   return o;
 }
 
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_sea
   const uint32_t slot = blockIdx.x;
   SlotScratch sc;
   {
-    size_t off[7];
-    slot_layout(L.node_cap, L.bnd_cap, L.ch_size, L.outs_cap, L.wf_cap, off);
+    size_t off[8];
+    slot_layout(L.node_cap, L.bnd_cap, L.ch_size, L.outs_cap, L.wf_cap, L.hist_cap, off);
     uint8_t* base = L.scratch + (size_t)slot * L.slot_bytes;
     sc.node_parent = reinterpret_cast<uint32_t*>(base + off[0]);
     sc.node_info = reinterpret_cast<uint32_t*>(base + off[1]);
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(NT, min_ctas<NT, BW, OUTC, FRAMES>()) beam_sea
     sc.wf = reinterpret_cast<FrameRec*>(base + off[3]);
     sc.wf_cap = L.wf_cap;
     sc.bnd = reinterpret_cast<BndRec*>(base + off[4]);
+    sc.hist = reinterpret_cast<HistRec*>(base + off[7]);
     sc.outs_g.key = reinterpret_cast<unsigned long long*>(base + off[5]);
     sc.outs_g.logit = reinterpret_cast<double*>(base + off[5] + (size_t)L.outs_cap * 8);
     sc.outs_g.order = reinterpret_cast<uint32_t*>(base + off[6]);
@@ -165,12 +167,14 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
   const uint64_t T = (uint64_t)std::max(1, L.P.T_max);
   const uint64_t bw = (uint64_t)L.P.beam_width;
   uint32_t node_cap = (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu);
-  uint32_t bnd_cap = L.lm.present ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
+  const bool need_bnd = L.lm.present || L.P.prune_history;
+  uint32_t bnd_cap = need_bnd ? (uint32_t)std::min<uint64_t>(bw * T + 64, (1u << 24) - 1) : 16;
+  uint32_t hist_cap = L.P.prune_history ? bnd_cap : 0u;
   uint32_t ch_size = (uint32_t)T + 16;  // floats of row-sum scratch (input classification)
   uint32_t outs_cap = (uint32_t)((bw * (uint64_t)(L.P.V + 1) + 64 + 3) & ~(uint64_t)3);
   uint32_t wf_cap = FRAMES ? (uint32_t)std::min<uint64_t>(bw * T + 64, 0x7FFFFFFFu) : 0u;
-  size_t off[7];
-  const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
+  size_t off[8];
+  const size_t slot_bytes = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, hist_cap, off);
   std::lock_guard<std::mutex> lock(dec->mu);
   coral_decoder::Scratch& S = dec->scratch[(void*)st];
   // the arena is reused as long as its per-slot capacities cover this launch and it has a slot
@@ -178,7 +182,7 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
   // (re)allocation queries the free memory
   uint32_t n_slots = want;
   const bool fits = S.d_scratch && S.node_cap >= node_cap && S.bnd_cap >= bnd_cap &&
-                    S.ch_size >= ch_size && S.outs_cap >= outs_cap && S.wf_cap >= wf_cap &&
+                    S.ch_size >= ch_size && S.outs_cap >= outs_cap && S.wf_cap >= wf_cap && S.hist_cap >= hist_cap &&
                     (S.n_slots >= want || S.budget_capped);
   if (fits) {
     // reuse the arena with the (larger) capacities it was laid out for
@@ -187,13 +191,16 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
     ch_size = S.ch_size;
     outs_cap = S.outs_cap;
     wf_cap = S.wf_cap;
+    hist_cap = S.hist_cap;
   } else {
     node_cap = std::max(node_cap, S.node_cap);
     bnd_cap = std::max(bnd_cap, S.bnd_cap);
     ch_size = std::max(ch_size, S.ch_size);
     outs_cap = std::max(outs_cap, S.outs_cap);
     wf_cap = std::max(wf_cap, S.wf_cap);
-    const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, off);
+    hist_cap = std::max(hist_cap, S.hist_cap);
+    if (hist_cap) hist_cap = std::max(hist_cap, bnd_cap);  // one history record per boundary record
+    const size_t sb = slot_layout(node_cap, bnd_cap, ch_size, outs_cap, wf_cap, hist_cap, off);
     size_t free_b = 0, total_b = 0;
     CORAL_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::min<size_t>((size_t)48 << 30, (free_b + S.scratch_bytes) / 2);
@@ -217,6 +224,7 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
     S.ch_size = ch_size;
     S.outs_cap = outs_cap;
     S.wf_cap = wf_cap;
+    S.hist_cap = hist_cap;
   }
   if (!S.d_work) CORAL_CUDA_OK(cudaMalloc(&S.d_work, 2 * sizeof(int32_t)));  // work counter, give-up flag
   CORAL_CUDA_OK(cudaMemsetAsync(S.d_work, 0, 2 * sizeof(int32_t), st));
@@ -227,6 +235,7 @@ static int32_t launch_beam_t(coral_decoder* dec, BeamLaunch& L, int32_t B, cudaS
   L.ch_size = ch_size;
   L.outs_cap = outs_cap;
   L.wf_cap = wf_cap;
+  L.hist_cap = hist_cap;
   L.work = S.d_work;
   const uint32_t grid = std::min<uint32_t>(S.n_slots, std::max<uint32_t>(1, want));
   kern<<<grid, NT, smem, st>>>(L);
@@ -356,7 +365,6 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
                                 std::to_string(dec->P.V) + ". Need logits of shape: (time, vocabulary)");
   if (beam_width < 1 || beam_width > 512) return fail(CORAL_EARG, "beam_width must be in [1, 512]");
   if (n_best < 1 || n_best > beam_width) return fail(CORAL_EARG, "n_best must be in [1, beam_width]");
-  if (prune_history) return fail(CORAL_EARG, "prune_history=True is not implemented (SURVEY 8f N4)");
   if (input_mode < 0 || input_mode > 2) return fail(CORAL_EARG, "input_mode must be 0, 1 or 2");
   if (B == 0) return CORAL_OK;
   if (!logits_dev || !lengths_dev || !out_n_beams_dev || !out_logit_score_dev || !out_lm_score_dev ||
@@ -372,6 +380,8 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   L.P.n_best = n_best;
   L.P.T_max = T_max > 0 ? T_max : 1;
   L.P.input_mode = input_mode;
+  // pyctcdecode _prune_history: min_n_history = max(1, lm_order - 1), lm_order = 1 without a language model
+  L.P.prune_history = prune_history ? std::max(1, (dec->lm ? dec->lm->host.order : 1) - 1) : 0;
   {
     // pinned host logits are read in place (zero-copy): plain loads + L2 prefetch of the next
     // frames (mode 2, default: measured 16.3 ms per 8192 utterances against 15.3 ms for

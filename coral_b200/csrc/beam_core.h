@@ -144,6 +144,7 @@ struct DecodeParams {
   int32_t T_max;        // row pitch of logits [B, T_max, V] and of out_tokens
   int32_t input_mode;   // 0 auto (pyctcdecode's test, evaluated per utterance), 1 logits, 2 probabilities
   int32_t host_input;   // logits live in pinned HOST memory: 1 = uncached loads, 2 = plain loads + L2 prefetch
+  int32_t prune_history;  // pyctcdecode prune_history=True: n = max(1, LM order - 1) words of history, 0 = off
   int32_t score_boundary;
   float token_min_logp;  // compared in float32
   double beam_prune_logp;
@@ -157,6 +158,14 @@ struct DecodeParams {
 struct BndRec {  // LM record of a word boundary (a complete-words text prefix)
   double lm_raw;
   LmState st;
+};
+
+// prune_history: the last words of a complete-words text prefix (64-bit hashes of the words, most
+// recent first, 0 = none) and the hash of the n most recent ones. One record per LM boundary
+// record (same index), kept in HBM and only when prune_history is on.
+struct HistRec {
+  unsigned long long H;
+  unsigned long long w[kMaxCtx];
 };
 
 // Candidates ("outputs") of one frame, struct-of-arrays so that ranking streams over a dense
@@ -185,6 +194,7 @@ struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after 
   uint32_t* node_parent;
   uint32_t* node_info;  // tok | bnd << 8
   BndRec* bnd;
+  HistRec* hist;        // [bnd_cap] with prune_history, else NULL
   OutView outs_g;       // overflow for frames with more candidates than fit in smem
   float* rowsum;        // [T_max] row sums of the utterance being classified
   uint32_t node_cap, bnd_cap, outs_cap;
@@ -870,9 +880,11 @@ struct BeamDecoder {
           // (what pyctcdecode caches under the new text in cached_lm_scores)
           uint32_t bnd_new = 0;
           double raw_new = sm.lm_raw[cur][rb];
-          if (lm.present) {
+          if (lm.present || P.prune_history) {
             bnd_new = atom_add(&sm.bnd_count, 1u);
             if (bnd_new >= sc.bnd_cap) { sm.status = -4; bnd_new = 0; }
+          }
+          if (lm.present) {
             const bool in_lm = (fl_m & kInLm) != 0;
             const bool oov = (lm.has_unigrams && !(fl_m & kInUni)) || !in_lm;
             BndRec nr;
@@ -1239,6 +1251,7 @@ struct BeamDecoder {
             sm.meta[nxt][r] = meta_pack(c, lc, kf >> 2);
           } else {
             const uint32_t bn = sm.o_aux[i];
+            if (P.prune_history) hist_push(sc, sm.bnd[cur][rb], bn, sm.whash[cur][rb], P.prune_history);
             sm.bnd[nxt][r] = bn;
             sm.wid[nxt][r] = 0;
             sm.whash[nxt][r] = kWordHashSeed;
@@ -1252,6 +1265,112 @@ struct BeamDecoder {
     }
     CORAL_GSYNC(NT);
     if (pt) pt->mark(13);
+  }
+
+  // ---- pyctcdecode prune_history=True (UP:pyctcdecode decoder.py _prune_history) ----
+  static CORAL_DEV_OUTLINE void hist_push(const SlotScratch& sc, uint32_t parent, uint32_t rec, unsigned long long word,
+                                          int n) {
+    HistRec h;
+    const HistRec& p = sc.hist[parent];
+    h.w[0] = word ? word : 1ULL;
+    for (int k = 1; k < kMaxCtx; ++k) h.w[k] = p.w[k - 1];
+    unsigned long long x = 0x6A09E667F3BCC909ULL;
+    for (int k = 0; k < n && k < kMaxCtx; ++k) x = mix64(x ^ h.w[k]) + 0x9E3779B97F4A7C15ULL;
+    h.H = x;
+    sc.hist[rec] = h;
+  }
+  // After the trim, in rank order: keep the first beam of every (last n words of the text,
+  // word_part, last_char). The beam list is compacted in place (read everything, barrier, write).
+  static CORAL_DEV_OUTLINE void prune_history_pass(Sm& sm, const DecodeParams& P, const SlotScratch& sc, int nxt, int q) {
+    const uint32_t S = sm.S[q] < (uint32_t)P.beam_width ? sm.S[q] : (uint32_t)P.beam_width;
+    CORAL_LANES(NT) {
+      for (uint32_t r = lane; r < S; r += NT) {
+        const uint32_t mt = sm.meta[nxt][r];
+        unsigned long long k = sc.hist[sm.bnd[nxt][r]].H;
+        k = mix64(k ^ sm.whash[nxt][r]) + (unsigned long long)sm.wlen[nxt][r] * 0x9E3779B97F4A7C15ULL;
+        k = mix64(k ^ (unsigned long long)meta_lc(mt));
+        sm.o_key[r] = k;
+      }
+    }
+    CORAL_GSYNC(NT);
+    CORAL_LANES(NT) {
+      for (uint32_t r = lane; r < S; r += NT) {
+        const unsigned long long k = sm.o_key[r];
+        uint32_t dup = 0;
+        for (uint32_t j = 0; j < r; ++j) dup |= sm.o_key[j] == k ? 1u : 0u;
+        sm.o_order[r] = dup ? 0u : 1u;
+      }
+    }
+    CORAL_GSYNC(NT);
+    // every lane handles the beams r = lane, lane + NT, ...: at most (BW + NT - 1) / NT of them
+    constexpr int PER = (BW + NT - 1) / NT;
+    double v_logit[PER], v_raw[PER];
+    unsigned long long v_wh[PER], v_nh[PER], v_ph[PER];
+    uint32_t v_node[PER], v_bnd[PER], v_wid[PER], v_meta[PER], v_dst[PER];
+    uint16_t v_wlen[PER];
+    int32_t v_p0[PER], v_p1[PER];
+    uint32_t v_hd[PER];
+#if defined(CORAL_HOSTSIM)
+    // lanes run one after the other on the host: stage through per-beam copies instead of registers
+    static thread_local double h_logit[BW], h_raw[BW];
+    static thread_local unsigned long long h_wh[BW], h_nh[BW], h_ph[BW];
+    static thread_local uint32_t h_node[BW], h_bnd[BW], h_wid[BW], h_meta[BW], h_dst[BW], h_hd[BW];
+    static thread_local uint16_t h_wlen[BW];
+    static thread_local int32_t h_p0[BW], h_p1[BW];
+    uint32_t kept = 0;
+    for (uint32_t r = 0; r < S; ++r) {
+      h_dst[r] = sm.o_order[r] ? kept++ : kNoNode;
+      h_logit[r] = sm.logit[nxt][r]; h_raw[r] = sm.lm_raw[nxt][r]; h_wh[r] = sm.whash[nxt][r];
+      h_nh[r] = sm.nh[nxt][r]; h_ph[r] = sm.ph[nxt][r]; h_node[r] = sm.node[nxt][r]; h_bnd[r] = sm.bnd[nxt][r];
+      h_wid[r] = sm.wid[nxt][r]; h_meta[r] = sm.meta[nxt][r]; h_wlen[r] = sm.wlen[nxt][r];
+      if constexpr (FRAMES) { h_p0[r] = sm.wf.pf0[nxt][r]; h_p1[r] = sm.wf.pf1[nxt][r]; h_hd[r] = sm.wf.head[nxt][r]; }
+    }
+    for (uint32_t r = 0; r < S; ++r) {
+      const uint32_t d = h_dst[r];
+      if (d == kNoNode) continue;
+      sm.logit[nxt][d] = h_logit[r]; sm.lm_raw[nxt][d] = h_raw[r]; sm.whash[nxt][d] = h_wh[r];
+      sm.nh[nxt][d] = h_nh[r]; sm.ph[nxt][d] = h_ph[r]; sm.node[nxt][d] = h_node[r]; sm.bnd[nxt][d] = h_bnd[r];
+      sm.wid[nxt][d] = h_wid[r]; sm.meta[nxt][d] = h_meta[r]; sm.wlen[nxt][d] = h_wlen[r];
+      if constexpr (FRAMES) { sm.wf.pf0[nxt][d] = h_p0[r]; sm.wf.pf1[nxt][d] = h_p1[r]; sm.wf.head[nxt][d] = h_hd[r]; }
+    }
+    sm.S[q] = kept;
+    (void)v_logit; (void)v_raw; (void)v_wh; (void)v_nh; (void)v_ph; (void)v_node; (void)v_bnd; (void)v_wid;
+    (void)v_meta; (void)v_dst; (void)v_wlen; (void)v_p0; (void)v_p1; (void)v_hd;
+#else
+    {
+      const int lane = (int)(threadIdx.x % NT);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const uint32_t r = (uint32_t)lane + (uint32_t)u * NT;
+        v_dst[u] = kNoNode;
+        if (r < S && sm.o_order[r]) {
+          uint32_t d = 0;
+          for (uint32_t j = 0; j < r; ++j) d += sm.o_order[j];
+          v_dst[u] = d;
+          v_logit[u] = sm.logit[nxt][r]; v_raw[u] = sm.lm_raw[nxt][r]; v_wh[u] = sm.whash[nxt][r];
+          v_nh[u] = sm.nh[nxt][r]; v_ph[u] = sm.ph[nxt][r]; v_node[u] = sm.node[nxt][r]; v_bnd[u] = sm.bnd[nxt][r];
+          v_wid[u] = sm.wid[nxt][r]; v_meta[u] = sm.meta[nxt][r]; v_wlen[u] = sm.wlen[nxt][r];
+          if constexpr (FRAMES) { v_p0[u] = sm.wf.pf0[nxt][r]; v_p1[u] = sm.wf.pf1[nxt][r]; v_hd[u] = sm.wf.head[nxt][r]; }
+        }
+      }
+      CORAL_GSYNC(NT);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const uint32_t d = v_dst[u];
+        if (d == kNoNode) continue;
+        ++mine;
+        sm.logit[nxt][d] = v_logit[u]; sm.lm_raw[nxt][d] = v_raw[u]; sm.whash[nxt][d] = v_wh[u];
+        sm.nh[nxt][d] = v_nh[u]; sm.ph[nxt][d] = v_ph[u]; sm.node[nxt][d] = v_node[u]; sm.bnd[nxt][d] = v_bnd[u];
+        sm.wid[nxt][d] = v_wid[u]; sm.meta[nxt][d] = v_meta[u]; sm.wlen[nxt][d] = v_wlen[u];
+        if constexpr (FRAMES) { sm.wf.pf0[nxt][d] = v_p0[u]; sm.wf.pf1[nxt][d] = v_p1[u]; sm.wf.head[nxt][d] = v_hd[u]; }
+      }
+      if (lane == 0) sm.S[q] = 0;
+      CORAL_GSYNC(NT);
+      if (mine) atom_add(&sm.S[q], mine);
+    }
+#endif
+    CORAL_GSYNC(NT);
   }
 
   static CORAL_DEV unsigned long long prune_key(Sm& sm, const DecodeParams& P, int q) {
@@ -1287,6 +1406,7 @@ struct BeamDecoder {
       pt.mark(10);
     }
     rank_and_commit(sm, lm, P, sc, cur, q, thr, false, &pt, t);
+    if (P.prune_history && sm.status == 0) prune_history_pass(sm, P, sc, cur ^ 1, q);
   }
 
   // ---- end of utterance ------------------------------------------------------
@@ -1462,6 +1582,16 @@ struct BeamDecoder {
         if constexpr (FRAMES) { sm.wf.pf0[0][0] = -1; sm.wf.pf1[0][0] = -1; sm.wf.head[0][0] = 0; sm.wf.count = 1; }
         sc.node_parent[0] = kNoNode;
         sc.node_info[0] = kNoTok;
+        if (P.prune_history) {
+          HistRec h0;
+          h0.H = 0x6A09E667F3BCC909ULL;
+          for (int k = 0; k < kMaxCtx; ++k) h0.w[k] = 0;
+          // the root's H must be what hist_push would produce from an empty window
+          unsigned long long x = 0x6A09E667F3BCC909ULL;
+          for (int k = 0; k < P.prune_history && k < kMaxCtx; ++k) x = mix64(x ^ 0ULL) + 0x9E3779B97F4A7C15ULL;
+          h0.H = x;
+          sc.hist[0] = h0;
+        }
         if (lm.present) {
           BndRec r0;
           r0.lm_raw = 0.0;

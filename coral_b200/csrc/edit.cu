@@ -13,6 +13,9 @@
 //     determined by the distance alone (SURVEY 7 hard part 3).
 // Integer work throughout; results are bit-exact against the oracle.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -131,9 +134,11 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
     const EditWork W = on_chip ? Ws : Wg;
     int n1 = 0, n2 = 0;
     int status = (r1 == r0) ? 1 : 0;
+    bool too_long = false;  // a string that does not fit the work area is reported, never truncated
     if (mode == CORAL_EDIT_TOKENS) {
-      n1 = (int)min((int64_t)W.cap, r1 - r0);
-      n2 = (int)min((int64_t)W.cap, h1 - h0);
+      too_long = r1 - r0 > W.cap || h1 - h0 > W.cap;
+      n1 = too_long ? 0 : (int)(r1 - r0);
+      n2 = too_long ? 0 : (int)(h1 - h0);
       for (int i = lane; i < n1; i += 32) W.tok1[i] = ref_cps[r0 + i];
       for (int i = lane; i < n2; i += 32) W.tok2[i] = hyp_cps[h0 + i];
     } else {
@@ -141,8 +146,9 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
       strip_range(ref_cps, r0, r1, lane, rs, re);
       strip_range(hyp_cps, h0, h1, lane, hs, he);
       if (mode == CORAL_EDIT_CHARS) {
-        n1 = (int)min((int64_t)W.cap, re - rs);
-        n2 = (int)min((int64_t)W.cap, he - hs);
+        too_long = re - rs > W.cap || he - hs > W.cap;
+        n1 = too_long ? 0 : (int)(re - rs);
+        n2 = too_long ? 0 : (int)(he - hs);
         for (int i = lane; i < n1; i += 32) W.tok1[i] = ref_cps[rs + i];
         for (int i = lane; i < n2; i += 32) W.tok2[i] = hyp_cps[hs + i];
       } else {
@@ -151,8 +157,9 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
         uint32_t* we1 = W.vp + W.cap;      // needs cap*(cap/32) >= 2*cap  <=> cap >= 64
         uint32_t* ws2 = W.vn;
         uint32_t* we2 = W.vn + W.cap;
-        n1 = min(W.cap, split_words(ref_cps, rs, re, lane, ws1, we1, r0, W.cap));
-        n2 = min(W.cap, split_words(hyp_cps, hs, he, lane, ws2, we2, h0, W.cap));
+        n1 = split_words(ref_cps, rs, re, lane, ws1, we1, r0, W.cap);
+        n2 = split_words(hyp_cps, hs, he, lane, ws2, we2, h0, W.cap);
+        if (n1 > W.cap || n2 > W.cap) { too_long = true; n1 = n2 = 0; }
         __syncwarp();
         // canonical id of a word = index (in ref ++ hyp order) of its first exact occurrence
         for (int k = lane; k < n1 + n2; k += 32) {
@@ -177,6 +184,7 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
       }
     }
     if (n1 == 0) status = 1;
+    if (too_long) status = 2;
     __syncwarp();
     // remove_common_affix
     int p = 0;
@@ -203,7 +211,12 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
     const uint32_t* a = W.tok1 + p;
     const uint32_t* b = W.tok2 + p;
     int S = 0, D = 0, I = 0;
-    if (m1 == 0 || m2 == 0) {
+    // rapidfuzz aligns directly only while 2 * len1 * len2 bits stay under 1 MiB (then it splits the
+    // problem Hirschberg-style, which may pick another optimal script): beyond that, refuse
+    if ((int64_t)m1 * m2 >= 4194304 && m1 >= 65 && m2 >= 10) status = 2;
+    if (status == 2) {
+      // reported through out_status; the counts are zeroed
+    } else if (m1 == 0 || m2 == 0) {
       D = m1;
       I = m2;
     } else {
@@ -268,14 +281,21 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
       o[0] = S;
       o[1] = D;
       o[2] = I;
-      o[3] = n1 - (S + D);
+      o[3] = status == 2 ? 0 : n1 - (S + D);
       out_status[pair] = status;
     }
   }
 }
 
-static uint8_t* g_edit_work[16] = {nullptr};
-static size_t g_edit_work_bytes[16] = {0};
+// Off-chip DP work areas for pairs longer than the on-chip buffers: one per (device, stream),
+// like the decoder's scratch arenas, so launches on different streams never share one. Grown
+// lazily after waiting for that stream's earlier launches; kept for the life of the process.
+struct EditArea {
+  uint8_t* ptr = nullptr;
+  size_t bytes = 0;
+};
+static std::mutex g_edit_mu;
+static std::map<std::pair<int, void*>, EditArea> g_edit_areas;
 
 }  // namespace coral
 
@@ -293,8 +313,10 @@ int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_
   if (n_pairs == 0) return CORAL_OK;
   if (!ref_begin_dev || !ref_end_dev || !hyp_begin_dev || !hyp_end_dev || !out_sdih_dev || !out_status_dev)
     return fail(CORAL_EARG, "coral_edit_counts: null buffer");
-  if (device < 0 || device >= 16) return fail(CORAL_EARG, "device index out of range");
-  if (max_len > 8192) return fail(CORAL_ECAP, "strings above 8192 code points are not supported");
+  if (device < 0) return fail(CORAL_EARG, "device index out of range");
+  if (max_len > 2048)
+    return fail(CORAL_ECAP, "strings above 2048 symbols are outside rapidfuzz's direct-alignment range "
+                            "(it switches to Hirschberg splitting there): not restated");
   DeviceGuard g(device);
   cudaStream_t st = (cudaStream_t)stream;
   const int sms = sm_count(device);
@@ -310,19 +332,26 @@ int32_t coral_edit_counts_spans(const uint32_t* ref_cps_dev, const int64_t* ref_
     const int cap = (int)std::max<int64_t>(64, (max_len + 31) / 32 * 32);
     const size_t stride = ((size_t)cap * 4 * 2 + ((size_t)cap + 32) * 4 + (size_t)cap * (cap / 32) * 4 * 2 + 15) & ~(size_t)15;
     const int64_t need = (n_pairs + WARPS - 1) / WARPS;
-    const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * 4);
+    // long strings: fewer resident warps keep the work area bounded (1 MiB per warp at 2048 symbols)
+    const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * (cap <= 512 ? 4 : 1));
     const size_t bytes = stride * WARPS * grid;
-    if (g_edit_work_bytes[device] < bytes) {
-      CORAL_CUDA_OK(cudaDeviceSynchronize());
-      if (g_edit_work[device]) cudaFree(g_edit_work[device]);
-      g_edit_work[device] = nullptr;
-      g_edit_work_bytes[device] = 0;
-      CORAL_CUDA_OK(cudaMalloc(&g_edit_work[device], bytes));
-      g_edit_work_bytes[device] = bytes;
+    uint8_t* work = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_edit_mu);
+      EditArea& A = g_edit_areas[std::make_pair(device, (void*)st)];
+      if (A.bytes < bytes) {
+        CORAL_CUDA_OK(cudaStreamSynchronize(st));  // earlier launches on this stream may still use the old area
+        if (A.ptr) cudaFree(A.ptr);
+        A.ptr = nullptr;
+        A.bytes = 0;
+        CORAL_CUDA_OK(cudaMalloc(&A.ptr, bytes));
+        A.bytes = bytes;
+      }
+      work = A.ptr;
     }
     edit_counts_kernel<true, 128, WARPS><<<grid, WARPS * 32, 0, st>>>(
         ref_cps_dev, ref_begin_dev, ref_end_dev, hyp_cps_dev, hyp_begin_dev, hyp_end_dev, n_pairs, mode,
-        out_sdih_dev, out_status_dev, g_edit_work[device], stride, cap);
+        out_sdih_dev, out_status_dev, work, stride, cap);
   }
   CORAL_CUDA_OK(cudaGetLastError());
   return CORAL_OK;

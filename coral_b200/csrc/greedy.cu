@@ -13,6 +13,9 @@
 // thread, so the other threads spend their instructions on the row scans only; about nine
 // CTAs per SM keep enough tiles in flight to cover the HBM latency.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -163,6 +166,150 @@ ctc_argmax_kernel(const float* __restrict__ logits, const int32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused greedy decode: argmax + repeat-collapse + blank-drop in ONE kernel, no ids round trip.
+//
+// Every CTA walks a sequence of tiles (utterance, 128-frame block); utterances are handed out by a
+// global counter, so the sequence is only known to the CTA's producer thread, which runs
+// kStages - 1 tiles ahead: it writes the tile descriptor into the stage's slot, issues one bulk
+// asynchronous copy (TMA) for the tile and moves on -- there is always a tile in flight while the
+// 128 consumer threads scan the rows of the current one (thread f = frame f). The collapse runs
+// tile by tile inside the utterance: keep[f] = id != blank && (first frame || id != previous id),
+// an exclusive scan over the CTA (ballots + four warp totals) gives the output slot, the id of the
+// tile's last frame and the running output length are carried to the next tile.
+constexpr int kStages = 3;
+
+struct TileDesc {
+  int u;        // utterance, -1 = no more work
+  int t0;       // first frame of the tile
+  int nfr;      // frames in the tile
+  int last;     // 1 = last tile of the utterance
+  unsigned lead;  // bytes between the 16-byte aligned copy start and the first row
+  int bulk;     // 1 = delivered by the bulk copy (wait on the mbarrier), 0 = cp.async fallback
+};
+
+__global__ void __launch_bounds__(kTileFrames)
+ctc_greedy_fused_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lengths, int B, int T_max, int V,
+                        int blank_id, int pad_fixup, int32_t* __restrict__ out_ids, int32_t* __restrict__ out_tokens,
+                        int32_t* __restrict__ out_lens, int* __restrict__ work, unsigned stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long full[kStages];
+  __shared__ TileDesc desc[kStages];
+  __shared__ int s_ids[2][kTileFrames];
+  __shared__ int s_wtot[2][kTileFrames / 32];
+  const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(logits);
+  const uintptr_t buf_hi = buf_lo + (size_t)B * T_max * V * sizeof(float);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+  __syncthreads();
+
+  // producer state (thread 0 only)
+  int pu = -1, pT = 0, pt0 = 0;
+  bool drained = false;
+  auto produce = [&](int s) {
+    // next tile of the current utterance, or the first tile of the next utterance with frames
+    if (!drained && (pu < 0 || pt0 >= pT)) {
+      for (;;) {
+        pu = atomicAdd(work, 1);
+        if (pu >= B) { drained = true; break; }
+        pT = lengths ? lengths[pu] : T_max;
+        pT = pT < 0 ? 0 : (pT > T_max ? T_max : pT);
+        pt0 = 0;
+        if (pT > 0) break;
+        out_lens[pu] = 0;  // an empty utterance has no tile
+      }
+    }
+    TileDesc d;
+    if (drained) {
+      d.u = -1; d.t0 = 0; d.nfr = 0; d.last = 1; d.lead = 0; d.bulk = 0;
+      desc[s] = d;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+      return;
+    }
+    d.u = pu; d.t0 = pt0;
+    d.nfr = pT - pt0 < kTileFrames ? pT - pt0 : kTileFrames;
+    d.last = pt0 + d.nfr >= pT;
+    const float* src = logits + ((size_t)pu * T_max + pt0) * V;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uintptr_t a0 = a & ~(uintptr_t)15;
+    d.lead = (unsigned)(a - a0);
+    const unsigned bytes = (d.lead + (unsigned)d.nfr * V * 4u + 15u) & ~15u;
+    d.bulk = (a0 >= buf_lo && a0 + bytes <= buf_hi) ? 1 : 0;
+    if (!d.bulk) d.lead = 0;
+    desc[s] = d;
+    if (d.bulk) {
+      mbar_expect_tx(&full[s], bytes);
+      bulk_g2s(smem + (size_t)s * stage_bytes, reinterpret_cast<const void*>(a0), bytes, &full[s]);
+    } else {
+      // a tile the 16-byte granular bulk copy must not touch: the consumers copy it themselves
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+    }
+    pt0 += d.nfr;
+  };
+  if (tid == 0)
+    for (int s = 0; s < kStages - 1; ++s) produce(s);
+
+  int carry = -1;   // id of the utterance's previous frame (uniform across the CTA)
+  int base = 0;     // tokens written so far for the utterance
+  unsigned phase_bits = 0;
+  for (int k = 0;; ++k) {
+    const int s = k % kStages;
+    if (tid == 0) produce((k + kStages - 1) % kStages);  // that stage was released by the barrier of tile k - 1
+    mbar_wait(&full[s], (phase_bits >> s) & 1u);
+    phase_bits ^= 1u << s;
+    const TileDesc d = desc[s];
+    if (d.u < 0) break;
+    unsigned char* stage = smem + (size_t)s * stage_bytes;
+    if (!d.bulk) {
+      issue_tile(logits + ((size_t)d.u * T_max + d.t0) * V, reinterpret_cast<float*>(stage), d.nfr * V);
+      __syncthreads();
+    }
+    const int par = k & 1;
+    int id = blank_id;
+    if (tid < d.nfr) {
+      const float* row = reinterpret_cast<const float*>(stage + d.lead) + (size_t)tid * V;
+      float best;
+      id = row_argmax(row, V, best);
+      if (pad_fixup && best == -100.0f) {  // "all -100 row -> pad" (R:src/coral/compute_metrics.py:66)
+        bool all_m100 = true;
+        for (int v = 0; v < V; ++v) all_m100 &= row[v] == -100.0f;
+        if (all_m100) id = blank_id;
+      }
+      if (out_ids) out_ids[(size_t)d.u * T_max + d.t0 + tid] = id;
+    }
+    s_ids[par][tid] = id;
+    // the previous frame's id: the neighbour lane, the previous warp's last lane, or the carry
+    int prev = __shfl_up_sync(0xffffffffu, id, 1);
+    bool keep = false;
+    unsigned m = 0;
+    // warps need each other's last id and totals: one barrier per tile, which also releases the
+    // stage (every row has been read) for the producer
+    __syncthreads();
+    if (lane == 0) prev = warp == 0 ? carry : s_ids[par][tid - 1];
+    keep = tid < d.nfr && id != blank_id && ((d.t0 == 0 && tid == 0) || id != prev);
+    m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_wtot[par][warp] = __popc(m);
+    // second, cheap barrier for the warp totals (4 ints)
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kTileFrames / 32; ++w) {
+      const int c = s_wtot[par][w];
+      before += w < warp ? c : 0;
+      total += c;
+    }
+    if (keep) out_tokens[(size_t)d.u * T_max + base + before + __popc(m & ((1u << lane) - 1u))] = id;
+    carry = s_ids[par][d.nfr - 1];
+    base += total;
+    if (d.last) {
+      if (tid == 0) out_lens[d.u] = base;
+      base = 0;
+      carry = -1;
+    }
+  }
+}
+
 // One warp per utterance: keep[t] = id != blank && (!group || t == 0 || id != ids[t-1]),
 // compacted with ballots (no block barriers). Safe in place: a chunk is loaded completely
 // before anything is stored, and stores never pass the read cursor.
@@ -219,6 +366,10 @@ int32_t coral_ctc_collapse(const int32_t* ids_dev, const int32_t* lengths_dev, i
   return CORAL_OK;
 }
 
+// per-(device, stream) work counters of the fused kernel
+static std::mutex g_greedy_mu;
+static std::map<std::pair<int, void*>, int*> g_greedy_work;
+
 int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, int32_t B, int32_t T_max, int32_t V,
                          int32_t blank_id, int32_t pad_fixup, int32_t* out_ids_dev, int32_t* out_tokens_dev,
                          int32_t* out_lens_dev, void* stream) {
@@ -226,28 +377,40 @@ int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, in
   if (B == 0) return CORAL_OK;
   if (!logits_dev || !out_tokens_dev || !out_lens_dev) return fail(CORAL_EARG, "coral_ctc_greedy: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t* ids = out_ids_dev ? out_ids_dev : out_tokens_dev;
-  if (T_max > 0) {
-    const size_t smem = (((size_t)kTileFrames * V * sizeof(float) + 15) & ~(size_t)15) + 32;
-    if (smem > 200 * 1024) return fail(CORAL_EARG, "vocabulary too large for the greedy kernel's tiles");
-    int dev = 0;
-    CORAL_CUDA_OK(cudaGetDevice(&dev));
-    // occupancy for this tile size, queried once per (device, shared-memory size)
-    static int cache_per_sm[64] = {0};
-    static size_t cache_smem[64] = {0};
-    int per_sm = (cache_smem[dev & 63] == smem) ? cache_per_sm[dev & 63] : 0;
-    if (per_sm == 0) {
-      CORAL_CUDA_OK(cudaFuncSetAttribute(ctc_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_argmax_kernel, kTileFrames, smem));
-      cache_per_sm[dev & 63] = per_sm;
-      cache_smem[dev & 63] = smem;
-    }
-    const long long n_tiles = (long long)B * ((T_max + kTileFrames - 1) / kTileFrames);
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(n_tiles, (long long)std::max(per_sm, 1) * sm_count(dev)));
-    ctc_argmax_kernel<<<grid, kTileFrames, smem, st>>>(logits_dev, lengths_dev, B, T_max, V, blank_id, pad_fixup, ids);
-    CORAL_CUDA_OK(cudaGetLastError());
+  if (T_max == 0) {
+    CORAL_CUDA_OK(cudaMemsetAsync(out_lens_dev, 0, sizeof(int32_t) * (size_t)B, st));
+    return CORAL_OK;
   }
-  return coral_ctc_collapse(ids, lengths_dev, B, T_max, blank_id, 1, out_tokens_dev, out_lens_dev, stream);
+  // one stage = 128 rows + up to 12 bytes of lead-in, rounded to 128 bytes
+  const size_t stage_bytes = (((size_t)kTileFrames * V * sizeof(float) + 16 + 127) / 128) * 128;
+  const size_t smem = stage_bytes * kStages;
+  if (smem > 200 * 1024) return fail(CORAL_EARG, "vocabulary too large for the greedy kernel's tiles");
+  int dev = 0;
+  CORAL_CUDA_OK(cudaGetDevice(&dev));
+  // occupancy for this tile size, queried once per (device, shared-memory size)
+  static int cache_per_sm[64] = {0};
+  static size_t cache_smem[64] = {0};
+  int per_sm = (cache_smem[dev & 63] == smem) ? cache_per_sm[dev & 63] : 0;
+  if (per_sm == 0) {
+    CORAL_CUDA_OK(cudaFuncSetAttribute(ctc_greedy_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CORAL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_greedy_fused_kernel, kTileFrames, smem));
+    cache_per_sm[dev & 63] = per_sm;
+    cache_smem[dev & 63] = smem;
+  }
+  int* work = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_greedy_mu);
+    int*& w = g_greedy_work[std::make_pair(dev, (void*)st)];
+    if (!w) CORAL_CUDA_OK(cudaMalloc(&w, sizeof(int)));
+    work = w;
+  }
+  CORAL_CUDA_OK(cudaMemsetAsync(work, 0, sizeof(int), st));
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(B, (long long)std::max(per_sm, 1) * sm_count(dev)));
+  ctc_greedy_fused_kernel<<<grid, kTileFrames, smem, st>>>(logits_dev, lengths_dev, B, T_max, V, blank_id, pad_fixup,
+                                                            out_ids_dev, out_tokens_dev, out_lens_dev, work,
+                                                            (unsigned)stage_bytes);
+  CORAL_CUDA_OK(cudaGetLastError());
+  return CORAL_OK;
 }
 
 }  // extern "C"

@@ -30,7 +30,7 @@ struct coral_decoder {
     size_t scratch_bytes = 0;
     size_t slot_bytes = 0;
     uint32_t n_slots = 0;
-    uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0, wf_cap = 0;
+    uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0, wf_cap = 0, hist_cap = 0;
     int32_t* d_work = nullptr;
     bool budget_capped = false;  // the memory budget, not the launch, limited n_slots
   };

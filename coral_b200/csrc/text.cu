@@ -13,6 +13,7 @@
 //     (HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:371, :398-406) is packed into ONE
 //     pinned, ragged [sum T_i, V] buffer by a few host threads; the beam kernel then reads the
 //     valid frames straight from it (frame_offsets_dev), so no padding is ever moved.
+#include <dlfcn.h>
 #include <string.h>
 
 #include <algorithm>
@@ -169,6 +170,33 @@ int32_t coral_host_pack_rows(const void* const* src, const int64_t* n_bytes, con
     for (auto& t : th) t.join();
   }
   return CORAL_OK;
+}
+
+// The transcripts as a Python list of str, built in one C loop from the flat buffer that came
+// back from the device (what pyctcdecode's decode_batch returns, UP:pyctcdecode decoder.py). The
+// CPython entry points are looked up in the running process (no link-time dependency: the
+// library still loads in a host without Python); the caller must hold the GIL, i.e. bind this
+// symbol through ctypes.PyDLL. `kind` = bytes per symbol (1: Latin-1, 4: UTF-32). Returns a new
+// reference, or NULL when no interpreter is present / an allocation failed.
+void* coral_py_string_list(const void* data, int32_t kind, const int64_t* offsets, int64_t n) {
+  typedef void* (*list_new_t)(ssize_t);
+  typedef int (*list_set_t)(void*, ssize_t, void*);
+  typedef void* (*from_kind_t)(int, const void*, ssize_t);
+  typedef void (*decref_t)(void*);
+  static list_new_t list_new = (list_new_t)dlsym(RTLD_DEFAULT, "PyList_New");
+  static list_set_t list_set = (list_set_t)dlsym(RTLD_DEFAULT, "PyList_SetItem");
+  static from_kind_t from_kind = (from_kind_t)dlsym(RTLD_DEFAULT, "PyUnicode_FromKindAndData");
+  static decref_t decref = (decref_t)dlsym(RTLD_DEFAULT, "Py_DecRef");
+  if (!list_new || !list_set || !from_kind || !decref || !offsets || n < 0 || (kind != 1 && kind != 4)) return nullptr;
+  void* list = list_new((ssize_t)n);
+  if (!list) return nullptr;
+  const char* base = static_cast<const char*>(data);
+  for (int64_t i = 0; i < n; ++i) {
+    void* s = from_kind(kind, base + offsets[i] * kind, (ssize_t)(offsets[i + 1] - offsets[i]));
+    if (!s) { decref(list); return nullptr; }
+    list_set(list, (ssize_t)i, s);  // steals the reference
+  }
+  return list;
 }
 
 }  // extern "C"

@@ -220,8 +220,6 @@ class BeamSearchDecoderCTC:
             raise ValueError(
                 "Input logits shape is %s, but vocabulary is size %s. "
                 "Need logits of shape: (time, vocabulary)" % (tuple(logits.shape[1:]), len(self._idx2vocab)))
-        if prune_history:
-            raise NotImplementedError("prune_history=True is not implemented yet (SURVEY.md section 8f N4)")
         if not 1 <= beam_width <= MAX_BEAM_WIDTH:
             raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
         n_best = max(1, min(int(n_best), int(beam_width)))
@@ -457,11 +455,16 @@ class BeamSearchDecoderCTC:
         o = off.tolist()
         total = o[-1]
         cps = d_cps[:total].cpu().numpy()                 # sync #2: exactly the code points
-        if self._latin1:  # every label is below U+0100 (CoRal's alphabet): one byte per symbol decodes faster
-            text = cps.astype(np.uint8).tobytes().decode("latin-1")
+        # one C loop over the flat buffer builds the list of str (coral_py_string_list); every label
+        # below U+0100 (CoRal's alphabet) goes through the one-byte kind, which CPython copies fastest
+        off_np = off.numpy()
+        if self._latin1:
+            flat = cps.astype(np.uint8)
+            strings = _lib.load().coral_py_string_list(flat.ctypes.data, 1, off_np.ctypes.data, B)
         else:
-            text = cps.view(np.uint32).tobytes().decode("utf-32-le", "surrogatepass")
-        out = DecodedTexts(text[a:b] for a, b in zip(o[:-1], o[1:]))
+            flat = np.ascontiguousarray(cps.view(np.uint32))
+            strings = _lib.load().coral_py_string_list(flat.ctypes.data, 4, off_np.ctypes.data, B)
+        out = DecodedTexts(strings)
         max_len = int(d_max.item()) if B else 0
         out._coral_dev = (d_cps[:total], d_off, max_len, ("decoded", next(DecodedTexts._tokens)))
         return out
@@ -515,8 +518,6 @@ class BeamSearchDecoderCTC:
         logits_list = list(logits_list)
         if not logits_list:
             return []
-        if prune_history:
-            raise NotImplementedError("prune_history=True is not implemented yet (SURVEY.md section 8f N4)")
         if not 1 <= beam_width <= MAX_BEAM_WIDTH:
             raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
         torch = _torch()

@@ -21,6 +21,16 @@ from .textio import encode_utf32
 
 MODE_TOKENS, MODE_CHARS, MODE_WORDS = 0, 1, 2
 
+# What an EMPTY reference does. The reference pins jiwer 4.0.0 (R:uv.lock:1204-1205); jiwer accepts
+# empty references since 3.1 and scores them as all-insertions (S = D = H = 0, I = len(hyp)), where
+# 3.0.x raised ValueError("one or more references are empty strings"). jiwer is not installable in
+# the build image, so this is restated from the upstream change log, not checked against the
+# package (tools/pin_oracle.py records the real behaviour wherever jiwer imports). Default: what
+# 4.0.0 does; CORAL_B200_EMPTY_REFERENCE=raise restores the 3.0.x error.
+import os as _os
+
+EMPTY_REFERENCE = _os.environ.get("CORAL_B200_EMPTY_REFERENCE", "allow")
+
 
 def _torch():
     import torch
@@ -134,7 +144,12 @@ def _pair_counts(preds, labs, kinds, device=None) -> dict:
         # one read-back for everything that was queued
         sdih = torch.stack([o[0] for o in outs]).cpu().numpy().astype(np.int64)
         status = torch.stack([o[1] for o in outs]).cpu().numpy()
-        if status.any():
+        if (status == 2).any():
+            _MEMO.clear()
+            i = int(np.nonzero((status == 2).any(axis=0))[0][0])
+            raise _lib.CoralError(_lib.ECAP, f"pair {i}: a string is longer than the declared maximum, or the pair is "
+                                             "outside rapidfuzz's direct-alignment range (len1 * len2 >= 2^22)")
+        if EMPTY_REFERENCE == "raise" and (status == 1).any():
             _MEMO.clear()
             raise ValueError("one or more references are empty strings")
         for k, a in zip(todo, sdih):

@@ -132,7 +132,12 @@ int32_t coral_decoder_info(const coral_decoder* dec, uint64_t* lexicon_entries, 
  *                   word_offsets, HF:...processing_wav2vec2_with_lm.py:416-443); with it,
  *   out_word_counts_dev  int32 [B, n_best] words written per beam. max_words >= (T_max + 1) / 2 + 1
  *                   holds every possible transcript. NULL selects the kernel without word timing.
- * prune_history != 0 and hotwords are not implemented: CORAL_EARG. */
+ * prune_history != 0 is pyctcdecode's prune_history=True: after every frame's trim only the best
+ * beam per (last max(1, LM order - 1) words of the text, word_part, last_char) stays.
+ * Hotwords are not implemented: pyctcdecode's HotwordScorer scores partial words through
+ * next(CharTrie.iterkeys(prefix, shallow=True)) over a trie built from a Python set, i.e. its
+ * result depends on set iteration order (not reproducible across processes), and CoRal never
+ * passes hotwords; the Python surface raises NotImplementedError for them. */
 int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const int32_t* lengths_dev,
                               const int32_t* order_dev, const int64_t* frame_offsets_dev, int32_t B,
                               int32_t T_max, int32_t V, int32_t beam_width, double beam_prune_logp, double token_min_logp,
@@ -167,6 +172,13 @@ int32_t coral_decoder_tokens_to_text(const coral_decoder* dec, const uint8_t* to
 int32_t coral_host_pack_rows(const void* const* src, const int64_t* n_bytes, const int64_t* dst_offsets,
                              int64_t n, void* dst, int32_t n_threads);
 
+/* HOST helper for Python hosts: n strings out of one flat buffer (kind = bytes per symbol: 1 Latin-1,
+ * 4 UTF-32; offsets [n + 1] in symbols) as a new Python list of str -- the list decode_batch returns
+ * (UP:pyctcdecode decoder.py). Resolves the CPython API in the running process at call time, so
+ * the library has no link-time dependency on Python; call it with the GIL held (ctypes.PyDLL).
+ * Returns a PyObject* (new reference) or NULL. */
+void* coral_py_string_list(const void* data, int32_t kind, const int64_t* offsets, int64_t n);
+
 /* -------------------------------------------------------------------- greedy (A3/A4) */
 
 /* np.argmax(axis=-1) + Wav2Vec2CTCTokenizer grouping (R:src/coral/compute_metrics.py:62-70;
@@ -195,8 +207,15 @@ int32_t coral_ctc_collapse(const int32_t* ids_dev, const int32_t* lengths_dev, i
 /* jiwer.process_characters / process_words -> rapidfuzz Levenshtein.editops counts
  * (R:src/coral/metrics.py:26-33, :54-61).
  *   out_sdih_dev   int32 [n_pairs, 4] = substitutions, deletions, insertions, hits
- *   out_status_dev int32 [n_pairs]   1 when the reference is empty (jiwer raises ValueError)
- *   max_len        upper bound on the code points of any one string (sizes on-chip buffers) */
+ *   out_status_dev int32 [n_pairs]   0; 1 = the reference is empty after the transform (counts are then
+ *                  S = D = H = 0, I = len(hyp): what jiwer >= 3.1 returns; jiwer 3.0 raised ValueError --
+ *                  the caller chooses, see coral_b200/metrics.py); 2 = a string exceeds max_len, or the
+ *                  pair is outside rapidfuzz's direct-alignment range (len1 * len2 >= 2^22 symbols:
+ *                  rapidfuzz switches to Hirschberg splitting there) -- its counts are zeroed, never
+ *                  computed on truncated input
+ *   max_len        upper bound on the code points of any one string (sizes the work areas;
+ *                  <= 2048, larger values return CORAL_ECAP)
+ * Launches on different streams use separate off-chip work areas (one per device and stream). */
 int32_t coral_edit_counts(const uint32_t* ref_cps_dev, const int64_t* ref_offsets_dev,
                           const uint32_t* hyp_cps_dev, const int64_t* hyp_offsets_dev, int64_t n_pairs,
                           int32_t mode, int64_t max_len, int32_t device, int32_t* out_sdih_dev,

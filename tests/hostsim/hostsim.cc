@@ -117,6 +117,8 @@ static int run_t(HsDecoder* d, const DecodeParams& P, const float* logits, int T
   sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 64);
   std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap);
   std::vector<BndRec> bnd(sc.bnd_cap);
+  std::vector<HistRec> hist(P.prune_history ? sc.bnd_cap : 1);
+  sc.hist = hist.data();
   std::vector<unsigned long long> g_key(sc.outs_cap);
   std::vector<double> g_logit(sc.outs_cap);
   std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
@@ -181,6 +183,12 @@ int hs_decode(void* h, const float* logits, int T, int is_prob, int beam_width, 
   P.score_boundary = score_boundary;
   P.token_min_logp = (float)token_min_logp;
   P.beam_prune_logp = beam_prune_logp;
+  {
+    // variant >= 100 selects prune_history=True on variant - 100 (keeps the C signature stable)
+    const bool ph = variant >= 100;
+    if (ph) variant -= 100;
+    P.prune_history = ph ? (d->has_lm ? (d->lm.order - 1 > 1 ? d->lm.order - 1 : 1) : 1) : 0;
+  }
   P.alpha = alpha;
   P.beta = beta;
   P.unk_score_offset = unk_score_offset;

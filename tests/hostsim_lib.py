@@ -81,7 +81,7 @@ class HostSim:
 
     def decode_beams(self, logits, beam_width=100, beam_prune_logp=-10.0, token_min_logp=-5.0, alpha=0.5,
                      beta=1.5, unk_score_offset=-10.0, score_boundary=True, input_mode=0, is_prob=None,
-                     variant=0, repeat=1, n_best=None, frames=False):
+                     variant=0, repeat=1, n_best=None, frames=False, prune_history=False):
         logits = np.ascontiguousarray(logits, dtype=np.float32)
         T, V = logits.shape
         if is_prob is None:
@@ -104,7 +104,8 @@ class HostSim:
         out_nwords = np.zeros(n_best, np.int32) if frames else None
         st = self.lib.hs_decode(
             self.h, logits.ctypes.data, T, int(is_prob), beam_width, beam_prune_logp, token_min_logp, alpha, beta,
-            unk_score_offset, int(score_boundary), LOG_BASE_CHANGE, input_mode, n_best, variant, repeat,
+            unk_score_offset, int(score_boundary), LOG_BASE_CHANGE, input_mode, n_best,
+            variant + (100 if prune_history else 0), repeat,
             out_n.ctypes.data, out_logit.ctypes.data, out_comb.ctypes.data, out_tok.ctypes.data,
             out_len.ctypes.data, stats.ctypes.data,
             out_frames.ctypes.data if frames else None, out_nwords.ctypes.data if frames else None, max_words)

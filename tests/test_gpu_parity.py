@@ -184,12 +184,64 @@ def test_cer_wer_and_errors(torch_cuda, rng):
     for norm in (True, False):
         assert metrics.cer(hyps, refs, norm) == oe.cer(hyps, refs, norm)
         assert metrics.wer(hyps, refs, norm) == oe.wer(hyps, refs, norm)
-    with pytest.raises(ValueError):
-        metrics.cer(["abc"], [""])
-    with pytest.raises(ValueError):
-        metrics.wer(["abc"], ["   "])
+    # an empty reference scores as all insertions (jiwer >= 3.1; the reference pins 4.0.0) ...
+    assert metrics.edit_counts(["abc", "x y"], ["", "   "], "chars").tolist() == [[0, 0, 3, 0], [0, 0, 3, 0]]
+    assert metrics.edit_counts(["abc", "x y"], ["", "   "], "words").tolist() == [[0, 0, 1, 0], [0, 0, 2, 0]]
+    assert metrics.cer(["abc", "de"], ["", "dx"]) == oe.cer(["abc", "de"], ["", "dx"]) == 4 / 5
+    with pytest.raises(ZeroDivisionError):   # ... and only an empty total divides by zero
+        metrics.cer(["abc"], [""], normalise=False)
     with pytest.raises(ZeroDivisionError):
         metrics.cer([], [])
+    # the jiwer 3.0.x behaviour is one switch away
+    import importlib
+    os.environ["CORAL_B200_EMPTY_REFERENCE"] = "raise"
+    try:
+        importlib.reload(metrics)
+        with pytest.raises(ValueError):
+            metrics.cer(["abc"], [""])
+        with pytest.raises(ValueError):
+            metrics.wer(["abc"], ["   "])
+    finally:
+        del os.environ["CORAL_B200_EMPTY_REFERENCE"]
+        importlib.reload(metrics)
+
+
+def test_edit_counts_capacity_is_reported_not_truncated(torch_cuda, rng):
+    """A string longer than the declared max_len is an error status, never a silently truncated
+    score; pairs beyond rapidfuzz's direct-alignment range are refused; launches on different
+    streams use their own off-chip work areas."""
+    from coral_b200 import _lib, metrics
+    from coral_b200.textio import encode_utf32
+    from oracle import edit as oe
+
+    torch = torch_cuda
+    refs = ["a" * 300 + "b", "kort", "x" * 140]
+    hyps = ["a" * 290 + "c", "kart", "x" * 150]
+    r_cps, r_off = encode_utf32(refs)
+    h_cps, h_off = encode_utf32(hyps)
+    d = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+    sdih, status = metrics.edit_counts_device(d(r_cps), d(r_off), d(h_cps), d(h_off), 3, 1, 160)  # under-declared
+    assert status.cpu().tolist() == [2, 0, 0] and sdih.cpu().tolist()[0] == [0, 0, 0, 0]
+    assert tuple(sdih.cpu().tolist()[1]) == oe.char_counts(refs[1], hyps[1])
+    with pytest.raises(_lib.CoralError):
+        metrics.edit_counts(["a" * 2100], ["b" * 2100], "chars")
+    # two streams, long strings (off-chip work areas), interleaved launches
+    n = 64
+    big_r = ["".join(rng.choice(list("abcdef "), size=int(rng.integers(200, 900)))) for _ in range(n)]
+    big_h = ["".join(rng.choice(list("abcdef "), size=int(rng.integers(200, 900)))) for _ in range(n)]
+    want = [oe.char_counts(r, h) for r, h in zip(big_r, big_h)]
+    bufs = [tuple(d(x) for x in (*encode_utf32(big_r), *encode_utf32(big_h))) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        for k, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                rc, ro, hc, ho = bufs[k]
+                outs.append(metrics.edit_counts_device(rc, ro, hc, ho, n, 1, 900))
+    torch.cuda.synchronize()
+    for sdih, status in outs:
+        assert [tuple(x) for x in sdih.cpu().tolist()] == want and not status.cpu().numpy().any()
 
 
 def test_get_score_df_and_validation(torch_cuda, rng):
@@ -331,6 +383,36 @@ def test_beam_search_no_lm_edge_cases_and_errors(torch_cuda, small_workload, rng
         g.decode_beams(np.zeros((2, 10, 46), np.float32))
     with pytest.raises(NotImplementedError):
         g.decode_beams(lg[0], hotwords=["hej"])
+
+
+def test_prune_history(gpu_decoder, oracle_decoder, small_workload, rng):
+    """pyctcdecode's prune_history=True on the device: every beam, text and word frames, == the oracle;
+    the text-only kernel agrees; without an LM the history is one word."""
+    import synth
+    from coral_b200.decoder import build_ctcdecoder
+    from oracle.beam import build_ctcdecoder as oracle_build
+
+    w = small_workload
+    lg = [w.logits[u, : w.lengths[u]] for u in range(8)] + [synth.flat_logits(40, rng)]
+    for bw in (100, 32, 200):
+        got = gpu_decoder.decode_beams_batch(None, lg, beam_width=bw, prune_history=True)
+        for x, g in zip(lg, got):
+            ref = oracle_decoder.decode_beams(x, beam_width=bw, prune_history=True)
+            beams_equal(ref, g)
+    one = gpu_decoder.decode_beams(lg[0], prune_history=True)
+    beams_equal(oracle_decoder.decode_beams(lg[0], prune_history=True), one)
+    pad = np.full((len(lg), max(x.shape[0] for x in lg), 46), -100.0, np.float32)
+    for i, x in enumerate(lg):
+        pad[i, : x.shape[0]] = x
+    out = gpu_decoder.decode_padded(pad, np.array([x.shape[0] for x in lg], np.int32), prune_history=True, n_best=100)
+    texts = gpu_decoder.tokens_to_text(out.tokens.reshape(len(lg) * 100, -1), out.lens.reshape(-1))
+    for u, x in enumerate(lg):
+        ref = oracle_decoder.decode_beams(x, prune_history=True)
+        g = [(texts[u * 100 + k], float(out.logit_score[u, k]), float(out.lm_score[u, k])) for k in range(int(out.n_beams[u]))]
+        beams_equal(ref, g)
+    g0, o0 = build_ctcdecoder(synth.CORAL_LABELS), oracle_build(synth.CORAL_LABELS)
+    for x in (lg[0], lg[-1]):
+        beams_equal(o0.decode_beams(x, prune_history=True), g0.decode_beams(x, prune_history=True))
 
 
 def test_hf_processor_with_lm_drop_in(gpu_decoder, oracle_decoder, small_workload, tmp_path):

@@ -246,3 +246,30 @@ def test_config_cells_device_logic(cell, utts):
 
 
 _SIMS = {}
+
+
+@pytest.mark.parametrize("variant", [4, 0, 8])
+def test_prune_history_matches_the_oracle(sim, oracle_decoder, small_workload, rng, variant):
+    """pyctcdecode prune_history=True (first beam per (last order-1 words, word_part, last_char) after
+    every trim) in the kernel logic == the oracle's _prune_history; with and without an LM."""
+    import synth
+    from hostsim_lib import HostSim
+
+    w = small_workload
+    bw = 64 if variant == 8 else 100
+    for u in range(5):
+        lg = w.logits[u, : w.lengths[u]]
+        ref = oracle_decoder.decode_beams(lg, beam_width=bw, prune_history=True)
+        for frames in (False, True):
+            beams_equal(ref, sim.decode_beams(lg, beam_width=bw, variant=variant, prune_history=True, frames=frames))
+        assert len(ref) <= len(oracle_decoder.decode_beams(lg, beam_width=bw))
+    flat = synth.flat_logits(40, rng)
+    beams_equal(oracle_decoder.decode_beams(flat, beam_width=bw, prune_history=True),
+                sim.decode_beams(flat, beam_width=bw, variant=variant, prune_history=True))
+    if variant == 4:
+        from oracle.beam import build_ctcdecoder as oracle_build
+
+        o = oracle_build(synth.CORAL_LABELS)
+        hs = HostSim(o._alphabet.labels)
+        for lg in (w.logits[0, : w.lengths[0]], flat):
+            beams_equal(o.decode_beams(lg, prune_history=True), hs.decode_beams(lg, variant=4, prune_history=True))

@@ -69,10 +69,19 @@ def test_edit_known_answers():
     assert by[("hej med dig", "hej  med   dig")]["words"] == [0, 0, 0, 3]   # WER collapses spaces
     assert by[("hej med dig", "hej  med   dig")]["chars"][2] == 3            # CER counts each one
     assert edit.cer(["ba"], ["ab"]) == 2 / 3 and edit.cer(["ba"], ["ab"], normalise=False) == 1.0
-    with pytest.raises(ValueError):
-        edit.cer(["x"], [""])
-    with pytest.raises(ValueError):
-        edit.wer(["x"], ["  "])
+    # an empty reference: all insertions under jiwer >= 3.1 (the reference pins 4.0.0), ValueError under 3.0.x
+    assert edit.char_counts("", "x y") == (0, 0, 3, 0) and edit.word_counts("  ", "x y") == (0, 0, 2, 0)
+    assert edit.cer(["x"], [""]) == 1.0
+    with pytest.raises(ZeroDivisionError):
+        edit.cer(["x"], [""], normalise=False)
+    edit.EMPTY_REFERENCE = "raise"
+    try:
+        with pytest.raises(ValueError):
+            edit.cer(["x"], [""])
+        with pytest.raises(ValueError):
+            edit.wer(["x"], ["  "])
+    finally:
+        edit.EMPTY_REFERENCE = "allow"
     with pytest.raises(ZeroDivisionError):
         edit.cer([], [])
 
