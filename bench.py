@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--shape", default="read_aloud", choices=["read_aloud", "conversation"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = the headline (default), 3 / 4 / 5 see bench_configs.py")
     return ap.parse_args()
 
 
@@ -503,16 +505,19 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         from coral_b200.greedy import greedy_decode_device
 
-        def timed(fn, n=7):
+        def timed(fn, n=20):
+            """Mean device time of n back-to-back launches (events around the whole train: a host
+            sync per launch would add the Python launch overhead to a ~100 us kernel)."""
             for _ in range(3):
                 fn()
-            ts = []
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
             for _ in range(n):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            return float(np.median(ts))
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
 
         g_ms = timed(lambda: greedy_decode_device(d_logits, d_len, blank_id=45))
         fr = int(wl.lengths.sum())
@@ -617,6 +622,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config != 2:
+        import bench_configs
+
+        bench_configs.run(args, rank, world, local_rank, ClockSampler)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -204,17 +204,52 @@ ctc_greedy_fused_kernel(const float* __restrict__ logits, const int32_t* __restr
     for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
   __syncthreads();
 
-  // producer state (thread 0 only)
+  // producer state (thread 0 only). Utterances are claimed from the global counter two claims ahead
+  // of their use: the atomic for claim k + 2 and the length load of claim k + 1 are issued when
+  // utterance k starts, so neither round trip (about a microsecond each, as long as a whole
+  // utterance takes to stream) is ever waited for. One utterance per claim keeps the tail short:
+  // a CTA never sits on more than three unprocessed utterances.
+  constexpr int kGrab = 1;
   int pu = -1, pT = 0, pt0 = 0;
   bool drained = false;
+  int b_u0 = 0, b_i = kGrab;                // current batch: first utterance, next index in it
+  int b_len[kGrab] = {0};
+  int n_u0 = 0, n_len[kGrab] = {0};         // next batch (lengths already requested)
+  int nn_u0 = 0;                            // the batch after that (just claimed)
+  auto load_lens = [&](int u0, int* len) {
+#pragma unroll
+    for (int j = 0; j < kGrab; ++j) {
+      const int u = u0 + j;
+      int T = u < B ? (lengths ? lengths[u] : T_max) : 0;
+      len[j] = T < 0 ? 0 : (T > T_max ? T_max : T);
+    }
+  };
+  if (tid == 0) {
+    b_u0 = atomicAdd(work, kGrab);
+    n_u0 = atomicAdd(work, kGrab);
+    nn_u0 = atomicAdd(work, kGrab);
+    load_lens(b_u0, b_len);
+    load_lens(n_u0, n_len);
+    b_i = 0;
+  }
   auto produce = [&](int s) {
     // next tile of the current utterance, or the first tile of the next utterance with frames
     if (!drained && (pu < 0 || pt0 >= pT)) {
       for (;;) {
-        pu = atomicAdd(work, 1);
+        if (b_i == kGrab) {  // rotate the batches and keep two claims in flight
+          b_u0 = n_u0;
+#pragma unroll
+          for (int j = 0; j < kGrab; ++j) b_len[j] = n_len[j];
+          n_u0 = nn_u0;
+          if (n_u0 < B) { load_lens(n_u0, n_len); nn_u0 = atomicAdd(work, kGrab); }
+          b_i = 0;
+        }
+        pu = b_u0 + b_i;
         if (pu >= B) { drained = true; break; }
-        pT = lengths ? lengths[pu] : T_max;
-        pT = pT < 0 ? 0 : (pT > T_max ? T_max : pT);
+        pT = b_len[0];
+#pragma unroll
+        for (int j = 1; j < kGrab; ++j) pT = b_i == j ? b_len[j] : pT;
+        ++b_i;
         pt0 = 0;
         if (pT > 0) break;
         out_lens[pu] = 0;  // an empty utterance has no tile
@@ -307,6 +342,12 @@ ctc_greedy_fused_kernel(const float* __restrict__ logits, const int32_t* __restr
       base = 0;
       carry = -1;
     }
+  }
+  // the last CTA to leave rewinds the claim counter for the next launch on this stream (saves a
+  // memset launch in front of a ~100 us kernel)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
   }
 }
 
@@ -401,10 +442,12 @@ int32_t coral_ctc_greedy(const float* logits_dev, const int32_t* lengths_dev, in
   {
     std::lock_guard<std::mutex> lock(g_greedy_mu);
     int*& w = g_greedy_work[std::make_pair(dev, (void*)st)];
-    if (!w) CORAL_CUDA_OK(cudaMalloc(&w, sizeof(int)));
+    if (!w) {  // {claim counter, CTAs finished}: zeroed once, rewound by every launch's last CTA
+      CORAL_CUDA_OK(cudaMalloc(&w, 2 * sizeof(int)));
+      CORAL_CUDA_OK(cudaMemsetAsync(w, 0, 2 * sizeof(int), st));
+    }
     work = w;
   }
-  CORAL_CUDA_OK(cudaMemsetAsync(work, 0, sizeof(int), st));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(B, (long long)std::max(per_sm, 1) * sm_count(dev)));
   ctc_greedy_fused_kernel<<<grid, kTileFrames, smem, st>>>(logits_dev, lengths_dev, B, T_max, V, blank_id, pad_fixup,
                                                             out_ids_dev, out_tokens_dev, out_lens_dev, work,

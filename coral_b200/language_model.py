@@ -32,6 +32,14 @@ from .textio import encode_utf32
 logger = logging.getLogger(__name__)
 
 
+def _is_kenlm_binary(path: str) -> bool:
+    try:
+        with open(path, "rb") as f:
+            return f.read(33) == b"mmap lm http://kheafield.com/code"
+    except OSError:
+        return False
+
+
 def _current_device() -> int:
     import torch
 
@@ -61,6 +69,34 @@ class KenlmModel:
         self.ngram_counts = [int(counts[i]) for i in range(self.order)]
         self.vocab_size = int(vocab.value)
         self.device_bytes = int(dbytes.value)
+        self.is_binary = _is_kenlm_binary(path)
+        if self.is_binary:
+            # the reader has never seen a file written by the real build_binary:
+            # it refuses anything whose structure does not add up, but say so loudly, and cross-check
+            # against the ARPA file when the two sit side by side
+            logger.warning(
+                "coral_b200: %s was read by a KenLM probing-binary reader that is NOT pinned against a real "
+                "build_binary file (none was available to test with). Structural checks passed; if the ARPA "
+                "file is at hand, put it next to the .bin (same stem) and it is cross-checked at load time.", path)
+            arpa = os.path.splitext(path)[0] + ".arpa"
+            if os.path.exists(arpa):
+                self._cross_check(arpa)
+
+    def _cross_check(self, arpa_path: str, n: int = 256) -> None:
+        """Scores of sentences made of the ARPA's own unigrams must be bit-identical between the
+        binary-built and the ARPA-built tables (same float32 numbers, same order of additions)."""
+        words = sorted(load_unigram_set_from_arpa(arpa_path) - {"<s>", "</s>", "<unk>"})[: 4 * n]
+        if not words:
+            return
+        sents = [words[i: i + 4] for i in range(0, len(words), 4)]
+        other = KenlmModel(arpa_path, self.device)
+        a, _ = self.score_sentences(sents)
+        b, _ = other.score_sentences(sents)
+        for s, x, y in zip(sents, a, b):
+            if not np.array_equal(x, y):
+                raise _lib.CoralError(_lib.EIO, f"KenLM binary {self.path} disagrees with {arpa_path} on {s}: "
+                                                f"{x.tolist()} != {y.tolist()}")
+        logger.info("coral_b200: %s agrees with %s on %d sentences", self.path, arpa_path, len(sents))
 
     def __deepcopy__(self, memo):
         return self

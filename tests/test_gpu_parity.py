@@ -678,6 +678,27 @@ def test_kenlm_binary_model_directory(gpu_decoder, oracle_decoder, small_lm, sma
     arpa = [f for f in os.listdir(lm_dir) if f.endswith(".arpa")]
     assert len(arpa) == 1
     write_probing_binary(ArpaModel.load(str(lm_dir / arpa[0])), str(lm_dir / "5gram.bin"))
+    # a binary with its ARPA next to it (same stem) is cross-checked at load time -- and refused when
+    # the two disagree (the reader is not pinned against a real build_binary file)
+    from coral_b200 import _lib
+    from coral_b200.language_model import KenlmModel
+
+    side = tmp_path / "side"
+    side.mkdir()
+    shutil.copy(lm_dir / "5gram.bin", side / "m.bin")
+    shutil.copy(lm_dir / arpa[0], side / "m.arpa")
+    assert KenlmModel(str(side / "m.bin")).is_binary
+    text = (side / "m.arpa").read_text().splitlines()
+    k0 = next(i for i, ln in enumerate(text) if ln.startswith("\\1-grams:")) + 1
+    k1 = next(i for i, ln in enumerate(text) if ln.startswith("\\2-grams:"))
+    for k in range(k0, k1):  # every unigram probability moves: any sentence now scores differently
+        f = text[k].split("\t")
+        if len(f) >= 2:
+            f[0] = "%.4f" % (float(f[0]) - 0.5)
+            text[k] = "\t".join(f)
+    (side / "m.arpa").write_text("\n".join(text) + "\n")
+    with pytest.raises(_lib.CoralError):
+        KenlmModel(str(side / "m.bin"))
     os.remove(lm_dir / arpa[0])
     dec = BeamSearchDecoderCTC.load_from_dir(str(d))
     assert dec._language_model._kenlm_model.order == gpu_decoder._language_model._kenlm_model.order

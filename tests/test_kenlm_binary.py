@@ -105,3 +105,27 @@ def test_python_wrapper_sniffs_the_magic(small_bin):
     with pytest.raises((_lib.CoralError, OSError, RuntimeError, ValueError)):
         _lib.check(lib.coral_lm_load_kenlm_binary(b"/nonexistent/file.bin", 0, ctypes.byref(h)))
     assert os.path.getsize(small_bin) > 1000
+
+
+def test_hand_assembled_binary_fixture_reads_like_its_arpa_twin():
+    """tests/golden/tiny_bigram.bin was assembled byte by byte from KenLM's published layout by
+    tests/golden/make_tiny_kenlm_bin.py, which shares no code with tests/kenlm_binary_writer.py or
+    with the reader: the reader must accept it and score exactly like the ARPA
+    twin, OOV words and both start states included. (Still not a file from the real build_binary.)"""
+    import os
+
+    from hostsim_lib import HostSim
+
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    assert os.path.getsize(os.path.join(g, "tiny_bigram.bin")) == 411
+    labels = ["", " ", "a", "b"]
+    arpa = HostSim(labels, os.path.join(g, "tiny_bigram.arpa"))
+    binary = HostSim(labels, os.path.join(g, "tiny_bigram.bin"), unigrams=["a", "b"])
+    for s in (["a", "b", "a"], ["b", "b"], ["a", "zz", "b"], ["b"], []):
+        for bos in (True, False):
+            x, ox = arpa.score_sentence(s, bos=bos)
+            y, oy = binary.score_sentence(s, bos=bos)
+            assert np.array_equal(x, y) and ox.tolist() == oy.tolist(), (s, bos)
+    got, _ = binary.score_sentence(["a", "b", "a"])
+    # hand-computed: p(a|<s>) = -0.2, p(b|a) = -0.3, p(a|b) = -0.45, p(</s>|a) = backoff(a) + p(</s>) = -0.25 - 0.8
+    assert np.allclose(got, [-0.2, -0.3, -0.45, -1.05], atol=1e-6)

@@ -33,7 +33,7 @@ def _undefined(path):
 
 def test_no_undefined_names_in_product_bench_and_tools():
     files = glob.glob(os.path.join(ROOT, "coral_b200", "**", "*.py"), recursive=True)
-    files += [os.path.join(ROOT, f) for f in ("bench.py", "__graft_entry__.py", "synth.py")]
+    files += [os.path.join(ROOT, f) for f in ("bench.py", "bench_configs.py", "__graft_entry__.py", "synth.py")]
     files += glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "*.py"))
     bad = {os.path.relpath(f, ROOT): u for f in files if (u := _undefined(f))}
     assert not bad, bad
