@@ -437,13 +437,15 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- where an end-to-end step spends its time (separate, untimed-for-the-headline pass with a
     # synchronisation after every phase; max over ranks)
-    def e2e_phases(n=3):
+    def e2e_phases(n=5):
+        """Per-phase wall clock of an end-to-end step with a synchronisation after every phase:
+        median over n repetitions, max over ranks."""
         acc = {}
 
         def mark(name, t_prev):
             torch.cuda.synchronize()
             now = time.perf_counter()
-            acc[name] = acc.get(name, 0.0) + (now - t_prev)
+            acc.setdefault(name, []).append(now - t_prev)
             return now
 
         for _ in range(n):
@@ -466,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
                 metrics.cer(texts, refs), metrics.wer(texts, refs)
             t_ = mark("cer + wer: both edit kernels, one read-back" + (", all-reduce" if world > 1 else ""), t_)
             assert bad == 0
-        v = torch.tensor([acc[k] / n * 1e3 for k in acc], dtype=torch.float64, device=dev)
+        v = torch.tensor([float(np.median(acc[k])) * 1e3 for k in acc], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
         return {k: round(float(x), 3) for k, x in zip(acc, v.cpu().tolist())}

@@ -106,7 +106,10 @@ def _to_device(strings, dev):
     held = getattr(strings, "_coral_dev", None)
     if held is not None and held[0].device == dev:
         return held[0], held[1], held[2]
-    cps, off = encode_utf32(strings)
+    try:
+        cps, off = encode_utf32(strings)
+    except TypeError as e:  # "".join refuses anything that is not a str
+        raise TypeError("predictions and references must be strings") from e
     max_len = int(np.diff(off).max()) if len(off) > 1 else 0
     d_cps = torch.from_numpy(cps.view(np.int32)).to(dev, non_blocking=True)
     d_off = torch.from_numpy(off).to(dev, non_blocking=True)
@@ -126,9 +129,6 @@ def _pair_counts(preds, labs, kinds, device=None) -> dict:
     n = len(preds)
     if n == 0:
         return {k: np.zeros((0, 4), dtype=np.int64) for k in kinds}
-    for s in labs:
-        if not isinstance(s, str):
-            raise TypeError("references must be strings")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
