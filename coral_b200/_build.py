@@ -17,9 +17,9 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcoral_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-CU_SOURCES = ["lm.cu", "beam.cu", "greedy.cu", "edit.cu", "text.cu"]
+CU_SOURCES = ["lm.cu", "beam.cu", "beam_frames.cu", "greedy.cu", "edit.cu", "text.cu"]
 CC_SOURCES = ["lm_host.cc", "normalise.cc"]
-HEADERS = ["lm_tables.h", "lm_host.h", "beam_core.h", "handles.h", "common.cuh", os.path.join("..", "..", "include", "coral_b200.h")]
+HEADERS = ["lm_tables.h", "lm_host.h", "beam_core.h", "beam_launch.cuh", "handles.h", "common.cuh", os.path.join("..", "..", "include", "coral_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -80,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stdout + r.stderr)
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB_PATH, objs):
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs])

@@ -45,6 +45,8 @@ inline unsigned long long atom_cas_u64(unsigned long long* p, unsigned long long
 }
 inline uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
 inline uint32_t atom_exch_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+inline uint32_t atom_add_u16(uint16_t* p, uint32_t v) { uint32_t o = *p; *p = (uint16_t)(o + v); return o; }
+inline void atom_or_u64(unsigned long long* p, unsigned long long v) { *p |= v; }
 #define CORAL_LANES(NT) for (int lane = 0; lane < (NT); ++lane)
 #define CORAL_GSYNC(NT) ((void)0)
 #define CORAL_WSYNC() ((void)0)
@@ -64,6 +66,15 @@ __device__ __forceinline__ unsigned long long atom_cas_u64(unsigned long long* p
 }
 __device__ __forceinline__ uint32_t atom_cas_u32(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
 __device__ __forceinline__ uint32_t atom_exch_u32(uint32_t* p, uint32_t v) { return atomicExch(p, v); }
+__device__ __forceinline__ void atom_or_u64(unsigned long long* p, unsigned long long v) { atomicOr(p, v); }
+// 16-bit counters packed two per word: add to the right half, return that half's old value
+__device__ __forceinline__ uint32_t atom_add_u16(uint16_t* p, uint32_t v) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  unsigned int* w = reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3);
+  const unsigned sh = (a & 2) ? 16u : 0u;
+  const unsigned old = atomicAdd(w, v << sh);
+  return (old >> sh) & 0xFFFFu;
+}
 template <int NT>
 __device__ __forceinline__ void group_sync() {
   if (NT == 32) {
@@ -194,9 +205,23 @@ struct SlotScratch {  // per thread-group arenas in HBM, reused utterance after 
   uint32_t* node_parent;
   uint32_t* node_info;  // tok | bnd << 8
   BndRec* bnd;
-  HistRec* hist;        // [bnd_cap] with prune_history, else NULL
   OutView outs_g;       // overflow for frames with more candidates than fit in smem
   float* rowsum;        // [T_max] row sums of the utterance being classified
+  // rarely used arenas sit right behind the overflow candidates (outs_g.info) and are addressed
+  // from there, so that they cost the hot path no registers:
+  //   hv_sorted u32 [outs_cap]  heavy frames: (upper-bound bin << 24 | item id), best bins first
+  //   hv_masks  u64 [1024]      heavy frames: per live-prefix-hash slot, the tokens whose extension is live
+  //   hist      HistRec [bnd_cap] with prune_history
+  static constexpr size_t kHvMaskBytes = 1024 * 8;
+  CORAL_HD uint32_t* hv_sorted() const { return outs_g.info + outs_cap; }
+  CORAL_HD unsigned long long* hv_masks() const {
+    return reinterpret_cast<unsigned long long*>(outs_g.info + 2 * (size_t)outs_cap);
+  }
+  //   hv_bin    u8  [outs_cap]  heavy frames: upper-bound bin of every item (0xFF = no candidate)
+  CORAL_HD uint8_t* hv_bin() const { return reinterpret_cast<uint8_t*>(hv_masks()) + kHvMaskBytes; }
+  CORAL_HD HistRec* hist() const {
+    return reinterpret_cast<HistRec*>(hv_bin() + (((size_t)outs_cap + 15) & ~(size_t)15));
+  }
   uint32_t node_cap, bnd_cap, outs_cap;
 };
 
@@ -239,9 +264,28 @@ struct WordFrames {
 template <int BW>
 struct WordFrames<BW, false> {};
 
-template <int BW, int OUTC, bool FRAMES = false>
+// cycle timers of selected device operations: only in the instrumented (STATS) instantiation
+template <bool STATS>
+struct OpTimers {
+  unsigned long long opc[8];  // tuning: cycles spent inside selected device operations
+  uint32_t opn[8];            //         and how many times each ran
+};
+template <>
+struct OpTimers<false> {};
+
+// heavy frames (expand_heavy): histogram of the items' score upper bounds, two buckets per bin;
+// only in the instantiations that contain the heavy-frame path
+template <bool HEAVY>
+struct HeavyArea {
+  uint16_t ubcnt[kNB / 2];
+};
+template <>
+struct HeavyArea<false> {};
+
+template <int BW, int OUTC, bool FRAMES = false, bool STATS = true, bool HEAVY = true>
 struct GroupShared {
   WordFrames<BW, FRAMES> wf;
+  OpTimers<STATS> tm;
   static constexpr int HS = BW <= 32 ? 64 : (BW <= 64 ? 128 : (BW <= 128 ? 256 : (BW <= 256 ? 512 : 1024)));  // >= 2 BW
   // beams, double buffered
   double logit[2][BW];
@@ -288,8 +332,7 @@ struct GroupShared {
   uint32_t gsum[16];
   int32_t status, utt, is_prob;
   uint32_t cnt[8];  // work counters of this utterance (flushed to UttIO::stats at its end)
-  unsigned long long opc[8];  // tuning: cycles spent inside selected device operations
-  uint32_t opn[8];            //         and how many times each ran
+  HeavyArea<HEAVY> hv;
 };
 
 CORAL_HD uint32_t meta_pack(uint32_t tok, uint32_t lc, uint32_t flags) { return tok | (lc << 8) | (flags << 16); }
@@ -405,9 +448,11 @@ CORAL_HD float np_pairwise_sum(const float* a, int n) {
 #define CORAL_OP_T0(on) const long long _t0 = (on) ? clock64() : 0
 #define CORAL_OP_T1(on, sm, slot)                                                      \
   do {                                                                                 \
-    if (on) {                                                                          \
-      atomicAdd(&(sm).opc[slot], (unsigned long long)(clock64() - _t0));               \
-      atomicAdd(&(sm).opn[slot], 1u);                                                  \
+    if constexpr (STATS) {                                                             \
+      if (on) {                                                                        \
+        atomicAdd(&(sm).tm.opc[slot], (unsigned long long)(clock64() - _t0));          \
+        atomicAdd(&(sm).tm.opn[slot], 1u);                                             \
+      }                                                                                \
     }                                                                                  \
   } while (0)
 #else
@@ -441,9 +486,13 @@ struct PhaseTimer {
   }
 };
 
-template <int NT, int BW, int OUTC, bool FRAMES = false, bool STATS = true>
+// HEAVY: the instantiation contains the heavy-frame path (expand_heavy). The production launch
+// runs a lean kernel without it (HEAVY = false: the hot per-frame loop keeps its register and
+// instruction-cache budget) that hands utterances with many kept tokens per frame to a second,
+// HEAVY kernel; the instrumented kernels and the host simulation are HEAVY only.
+template <int NT, int BW, int OUTC, bool FRAMES = false, bool STATS = true, bool HEAVY = true>
 struct BeamDecoder {
-  using Sm = GroupShared<BW, OUTC, FRAMES>;
+  using Sm = GroupShared<BW, OUTC, FRAMES, STATS, HEAVY>;
   // work counters and cycle timers exist only in the STATS instantiation: in the default one
   // this is a compile-time null and everything that hangs off it folds away
   static CORAL_DEV unsigned long long* stats_of(const UttIO& io) { return STATS ? io.stats : nullptr; }
@@ -470,6 +519,11 @@ struct BeamDecoder {
     return 0;
   }
   static constexpr int HS = Sm::HS;
+  // items (live prefixes x (kept tokens + 1)) above which a frame takes the heavy path
+#ifndef CORAL_HEAVY_FACTOR
+#define CORAL_HEAVY_FACTOR 3
+#endif
+  static constexpr uint32_t kHeavyItems = (uint32_t)CORAL_HEAVY_FACTOR * (uint32_t)OUTC;
 
   // ---- live-node hash (shared memory), keyed by the prefix hash ------------------------
   static CORAL_DEV int h_find(Sm& sm, unsigned long long key) {
@@ -927,12 +981,14 @@ struct BeamDecoder {
           emit(sm, outs, sc.outs_cap, q, bscale, d_add(logit, d_add(sm.lm_raw[cur][rb], ps)), logit, order, nwid, 0u, rb, c,
                2u | (nfl << 2), lmax, mem[nm - 1]);
 #if defined(__CUDA_ARCH__)
-          if (tim) {
-            const long long tE = clock64();
-            atomicAdd(&sm.opc[0], (unsigned long long)(tB - tA)); atomicAdd(&sm.opn[0], 1u);
-            atomicAdd(&sm.opc[2], (unsigned long long)(tC - tB));
-            atomicAdd(&sm.opc[4], (unsigned long long)(tD - tC));
-            atomicAdd(&sm.opc[7], (unsigned long long)(tE - tD));
+          if constexpr (STATS) {
+            if (tim) {
+              const long long tE = clock64();
+              atomicAdd(&sm.tm.opc[0], (unsigned long long)(tB - tA)); atomicAdd(&sm.tm.opn[0], 1u);
+              atomicAdd(&sm.tm.opc[2], (unsigned long long)(tC - tB));
+              atomicAdd(&sm.tm.opc[4], (unsigned long long)(tD - tC));
+              atomicAdd(&sm.tm.opc[7], (unsigned long long)(tE - tD));
+            }
           }
 #endif
         }
@@ -971,6 +1027,241 @@ struct BeamDecoder {
         while (ch >= nchunks) { ch -= nchunks; ++g; }
       }
       if (lmax) atom_max_u64(&sm.gmax[q], lmax);
+    }
+    CORAL_GSYNC(NT);
+  }
+
+  // ---- heavy frames: many kept tokens (flat posteriors, loose token_min_logp) ----------------
+  // nN x (K + 1) items, of which only beam_width can survive. Instead of expanding all of them,
+  // the items are visited in the order of a cheap UPPER BOUND of their score (the threshold
+  // algorithm of top-k query processing):
+  //   A. every item: members through the live-prefix hash (as in expand_item), upper bound
+  //      ub = max member logit + ln(#members) + p + an upper bound of the LM part (exact for
+  //      blank / repeat / merge items; "no partial-word penalty" for a letter; alpha * (unk) *
+  //      ln10 + beta for a word that closes) -> histogram of upper-bound bins;
+  //   B. counting sort of the items by bin (best first) into the slot's HBM scratch;
+  //   C. chunks of NT items in that order go through expand_item (the exact, expensive work:
+  //      lexicon probe, LM scoring, log-sum-exp). After each chunk: as soon as beam_width exact
+  //      candidates sit in buckets strictly better than the best remaining upper bound -- or that
+  //      bound is below the prune threshold -- no remaining item can survive, and the frame is done.
+  // Exact: ub >= true score item by item, the bucket map is monotone, and ranking / pruning only
+  // ever look at candidates that could make the cut.
+  static constexpr uint32_t kNoBin = 0xFFu;
+  static_assert(HS <= 1024, "SlotScratch::hv_masks holds 1024 slots");
+  // What the bound of an item needs to know about its live prefix, fetched once per prefix.
+  struct HeavyNode {
+    double l0, l1;        // logit of the member ending in a blank / in the prefix's last token (-inf: none)
+    double u_ab, u_a;     // max + ln(n) + 1e-6 over {b0, b1} and over {b0} alone (-inf: no member)
+    double own;           // LM part of the unchanged text: lm_raw + partial-word score
+    double lm_raw, pen1;  // raw LM score; partial-word penalty of one more (one-code-point) letter
+    unsigned long long ok, child_live;
+    uint32_t rb, tok_m, fl_m, wlen_m, b0, b1;
+    int s;
+    bool ok_known, parent_live;
+  };
+  static CORAL_DEV void heavy_node_setup(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                                         int cur, uint32_t j, HeavyNode& n) {
+    n.s = sm.ne_slot[j];
+    n.rb = rep_beam(sm, n.s);
+    const uint32_t mt = sm.meta[cur][n.rb];
+    n.tok_m = meta_tok(mt); n.fl_m = meta_flags(mt); n.wlen_m = sm.wlen[cur][n.rb];
+    n.b0 = sm.sb0[n.s]; n.b1 = sm.sb1[n.s];
+    n.l0 = n.b0 != kNone16 ? sm.logit[cur][n.b0] : -INFINITY;
+    n.l1 = n.b1 != kNone16 ? sm.logit[cur][n.b1] : -INFINITY;
+    // + 1e-6: the sequential fp64 log-sum-exp may round a hair above max + ln(n)
+    n.u_a = n.l0 + 1e-6;
+    n.u_ab = (n.l0 > n.l1 ? n.l0 : n.l1) + ((n.b0 != kNone16 && n.b1 != kNone16) ? 0.6931471805599454 : 0.0) + 1e-6;
+    n.lm_raw = sm.lm_raw[cur][n.rb];
+    n.own = d_add(n.lm_raw, partial_score(P, n.wlen_m, n.fl_m));
+    n.pen1 = lm.present ? partial_score(P, n.wlen_m + 1u, kOovPartial) : 0.0;
+    // tokens whose label keeps the partial word penalty-free (exact, from the lexicon's child mask)
+    n.ok = ~0ULL;
+    n.ok_known = false;
+    if (lm.present && lm.lex_ok != nullptr && !(n.fl_m & kDead)) {
+      n.ok_known = true;
+      if (n.wlen_m == 0) n.ok = lm.root_ok;
+      else {
+        const long long sl = lex_slot(lm, sm.whash[cur][n.rb]);
+        n.ok = sl >= 0 ? lm.lex_ok[sl] : 0ULL;
+      }
+    }
+    n.parent_live = n.tok_m != kNoTok && h_find(sm, sm.ph[cur][n.rb]) >= 0;
+    n.child_live = sc.hv_masks()[n.s];
+  }
+  // the rare item kinds: repeat family, space, a letter whose extended prefix is live already
+  static CORAL_DEV_OUTLINE double heavy_ub_general(Sm& sm, const LmView& lm, const DecodeParams& P, const HeavyNode& n,
+                                                   int f, int cur, int K, bool fam2, uint32_t c) {
+    static const double kLn[5] = {0.0, 0.0, 0.6931471805599454, 1.0986122886681098, 1.3862943611198906};
+    int nm = 0;
+    double mx = -INFINITY, lm_ub = n.own;
+    if (fam2) {
+      if (n.parent_live) return -INFINITY;
+      bool kept = false;
+      for (int kk = 0; kk < K; ++kk) kept |= sm.kept[f][kk] == c;
+      if (!kept) return -INFINITY;
+      if (n.b1 != kNone16) { ++nm; mx = n.l1; }
+      if ((int)c == P.space_id && n.b0 != kNone16) { ++nm; mx = n.l0 > mx ? n.l0 : mx; }
+    } else {
+      if ((int)c == P.space_id && n.wlen_m == 0) return -INFINITY;
+      if (n.b0 != kNone16) { ++nm; mx = n.l0; }
+      if (n.b1 != kNone16 && n.tok_m != c) { ++nm; mx = n.l1 > mx ? n.l1 : mx; }
+      const int cs = ((n.child_live >> c) & 1ULL) ? h_find(sm, child_hash(sm.nh[cur][n.rb], c)) : -1;
+      if (cs >= 0) {
+        const uint32_t c1 = sm.sb1[cs], c0 = sm.sb0[cs];
+        if (c1 != kNone16) { ++nm; const double v = sm.logit[cur][c1]; mx = v > mx ? v : mx; }
+        if ((int)c == P.space_id && c0 != kNone16) { ++nm; const double v = sm.logit[cur][c0]; mx = v > mx ? v : mx; }
+        const uint32_t crb = rep_beam(sm, cs);
+        lm_ub = d_add(sm.lm_raw[cur][crb], partial_score(P, sm.wlen[cur][crb], meta_flags(sm.meta[cur][crb])));
+      } else if ((int)c == P.space_id) {
+        lm_ub = n.lm_raw;
+        if (lm.present) {
+          if (P.alpha < 0.0) return INFINITY;  // no upper bound on alpha * log p: visit it first
+          const bool oov = (lm.has_unigrams && !(n.fl_m & kInUni)) || !(n.fl_m & kInLm);
+          // the word scores at most alpha * (log10 p upper bound + unk offset if OOV) * ln10 + beta
+          const double x = d_add((double)lm.score_ub, oov ? P.unk_score_offset : 0.0);
+          lm_ub = d_add(lm_ub, d_add(d_mul(d_mul(P.alpha, x), P.log_base_change), P.beta));
+        }
+      } else {
+        lm_ub = n.lm_raw;
+        if (lm.present) {
+          const bool penal = (n.fl_m & kDead) || (n.ok_known && !((n.ok >> c) & 1ULL));
+          if (penal || (!n.ok_known && P.unk_score_offset > 0.0))
+            lm_ub = d_add(lm_ub, partial_score(P, n.wlen_m + P.label_ncp[c], kOovPartial));
+        }
+      }
+    }
+    if (nm == 0) return -INFINITY;
+    return mx + kLn[nm] + (double)sm.lp[f][c] + lm_ub + 1e-6;
+  }
+  // upper-bound bin of item (prefix n, token group g); kNoBin = the item produces no candidate
+  static CORAL_DEV uint32_t heavy_bin(Sm& sm, const LmView& lm, const DecodeParams& P, const HeavyNode& n, int f,
+                                      int cur, int K, uint32_t g, double bscale) {
+    double ub;
+    if (g == (uint32_t)K) {
+      ub = heavy_ub_general(sm, lm, P, n, f, cur, K, true, n.tok_m == kNoTok ? (uint32_t)P.space_id : n.tok_m);
+    } else {
+      const uint32_t c = sm.kept[f][g];
+      if ((int)c == P.blank_id) {
+        ub = n.u_ab + (double)sm.lp[f][c] + n.own;                     // -inf when the prefix has no member at all
+      } else if ((int)c == P.space_id || ((n.child_live >> c) & 1ULL) || P.label_ncp[c] != 1) {
+        ub = heavy_ub_general(sm, lm, P, n, f, cur, K, false, c);
+      } else {
+        // a plain letter onto a prefix that is not live yet: members b0 (+ b1 unless it repeats c)
+        const double u = n.tok_m == c ? n.u_a : n.u_ab;
+        const bool penal = lm.present && ((n.fl_m & kDead) || (n.ok_known && !((n.ok >> c) & 1ULL)) ||
+                                          (!n.ok_known && P.unk_score_offset > 0.0));
+        ub = u + (double)sm.lp[f][c] + n.lm_raw + (penal ? n.pen1 : 0.0);
+      }
+    }
+    if (!(ub > -INFINITY)) return kNoBin;
+    return bucket_of(sm.mhat, bscale, ub) >> 1;
+  }
+
+  static CORAL_DEV_OUTLINE void expand_heavy(Sm& sm, const LmView& lm, const DecodeParams& P, const SlotScratch& sc,
+                                             const UttIO& io, int f, int cur, int q, uint32_t nb, const OutView& outs) {
+    const int K = sm.nkept[f];
+    const double bscale = bucket_scale(P);
+    const uint32_t nN = sm.nN[q];
+    constexpr int kBins = kNB / 2;
+    uint32_t* sorted = sc.hv_sorted();
+    CORAL_LANES(NT) {
+      if (lane == 0) {
+        sm.nN[q ^ 1] = 0; sm.n_out[q ^ 1] = 0; sm.S[q ^ 1] = 0; sm.gmax[q ^ 1] = 0;
+        if (stats_of(io)) { sm.cnt[0] += (uint32_t)K * nb; sm.cnt[3] += 1u; }
+      }
+      for (int i = lane; i < kBins; i += NT) sm.hv.ubcnt[i] = 0;
+      for (int i = lane; i < HS; i += NT) sc.hv_masks()[i] = 0ULL;
+    }
+    CORAL_GSYNC(NT);
+    // A0. every live prefix tells its (live) parent which token leads to it: nN hash look-ups
+    // instead of one per (prefix, kept token)
+    CORAL_LANES(NT) {
+      for (uint32_t j = (uint32_t)lane; j < nN; j += NT) {
+        const uint32_t rb = rep_beam(sm, sm.ne_slot[j]);
+        const uint32_t tok = meta_tok(sm.meta[cur][rb]);
+        if (tok == kNoTok) continue;
+        const int sp = h_find(sm, sm.ph[cur][rb]);
+        if (sp >= 0) atom_or_u64(&sc.hv_masks()[sp], 1ULL << tok);
+      }
+    }
+    CORAL_GSYNC(NT);
+    // A. upper-bound bin of every item (one live prefix per thread), kept for the scatter below
+    uint8_t* bins = sc.hv_bin();
+    const uint32_t M = ((uint32_t)K + 1u) * nN;
+    CORAL_LANES(NT) {
+      for (uint32_t j = (uint32_t)lane; j < nN; j += NT) {
+        HeavyNode n;
+        heavy_node_setup(sm, lm, P, sc, cur, j, n);
+        for (uint32_t g = 0; g <= (uint32_t)K; ++g) {
+          const uint32_t bin = heavy_bin(sm, lm, P, n, f, cur, K, g, bscale);
+          bins[g * nN + j] = (uint8_t)bin;
+          if (bin != kNoBin) atom_add_u16(&sm.hv.ubcnt[bin], 1u);
+        }
+      }
+    }
+    CORAL_GSYNC(NT);
+    // B. bin counts -> start offsets (warp 0: two bins per lane + a shuffle scan), then the item ids
+    // in the order of their bins
+    CORAL_LANES(NT) {
+#if defined(__CUDA_ARCH__)
+      static_assert(kBins == 64, "two upper-bound bins per lane");
+      if (lane < 32) {
+        const uint32_t c0 = sm.hv.ubcnt[2 * lane], c1 = sm.hv.ubcnt[2 * lane + 1];
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const uint32_t excl = incl - (c0 + c1);
+        sm.hv.ubcnt[2 * lane] = (uint16_t)excl;
+        sm.hv.ubcnt[2 * lane + 1] = (uint16_t)(excl + c0);
+        if (lane == 31) sm.sel_n = incl;  // items that produce a candidate at all
+      }
+#else
+      if (lane == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < kBins; ++b) { const uint32_t c = sm.hv.ubcnt[b]; sm.hv.ubcnt[b] = (uint16_t)run; run += c; }
+        sm.sel_n = run;
+      }
+#endif
+    }
+    CORAL_GSYNC(NT);
+    const uint32_t Mv = sm.sel_n;
+    CORAL_LANES(NT) {
+      for (uint32_t it = (uint32_t)lane; it < M; it += NT) {
+        const uint32_t bin = bins[it];
+        if (bin != kNoBin) sorted[atom_add_u16(&sm.hv.ubcnt[bin], 1u)] = (bin << 24) | it;
+      }
+    }
+    CORAL_GSYNC(NT);
+    // C. exact expansion in upper-bound order, one chunk of NT items at a time, until nothing that
+    // is left can survive
+    for (uint32_t base = 0; base < Mv; base += NT) {
+      CORAL_LANES(NT) {
+        unsigned long long lmax = 0;
+        const uint32_t at = base + (uint32_t)lane;
+        if (at < Mv) {
+          const uint32_t it = sorted[at] & 0xFFFFFFu;
+          const uint32_t g = it / nN, j = it - g * nN;
+          expand_item(sm, lm, P, sc, io, f, cur, q, nb, outs, bscale, K, g == (uint32_t)K, j, g, lmax);
+        }
+        if (lmax) atom_max_u64(&sm.gmax[q], lmax);
+      }
+      CORAL_GSYNC(NT);
+      if (sm.status != 0) return;
+      const uint32_t next = base + NT;
+      if (next >= Mv) break;
+      // the best upper bound still unvisited, as an exact-bucket index and as a score
+      const uint32_t nbkt = (sorted[next] >> 24) * 2u;
+      const double ub_score = d_add(sm.mhat, -d_div((double)nbkt, bscale));  // every score in bucket >= nbkt is <= this
+      bool done = ordered_u64(ub_score) < prune_key(sm, P, q) && nbkt > 0;
+      if (!done) {
+        uint32_t cum = 0;
+        for (uint32_t b = 0; b < nbkt && b < (uint32_t)kNB; ++b) cum += sm.bcnt[b];
+        done = cum >= (uint32_t)P.beam_width;
+      }
+      if (done) break;
     }
     CORAL_GSYNC(NT);
   }
@@ -1271,13 +1562,13 @@ struct BeamDecoder {
   static CORAL_DEV_OUTLINE void hist_push(const SlotScratch& sc, uint32_t parent, uint32_t rec, unsigned long long word,
                                           int n) {
     HistRec h;
-    const HistRec& p = sc.hist[parent];
+    const HistRec& p = sc.hist()[parent];
     h.w[0] = word ? word : 1ULL;
     for (int k = 1; k < kMaxCtx; ++k) h.w[k] = p.w[k - 1];
     unsigned long long x = 0x6A09E667F3BCC909ULL;
     for (int k = 0; k < n && k < kMaxCtx; ++k) x = mix64(x ^ h.w[k]) + 0x9E3779B97F4A7C15ULL;
     h.H = x;
-    sc.hist[rec] = h;
+    sc.hist()[rec] = h;
   }
   // After the trim, in rank order: keep the first beam of every (last n words of the text,
   // word_part, last_char). The beam list is compacted in place (read everything, barrier, write).
@@ -1286,7 +1577,7 @@ struct BeamDecoder {
     CORAL_LANES(NT) {
       for (uint32_t r = lane; r < S; r += NT) {
         const uint32_t mt = sm.meta[nxt][r];
-        unsigned long long k = sc.hist[sm.bnd[nxt][r]].H;
+        unsigned long long k = sc.hist()[sm.bnd[nxt][r]].H;
         k = mix64(k ^ sm.whash[nxt][r]) + (unsigned long long)sm.wlen[nxt][r] * 0x9E3779B97F4A7C15ULL;
         k = mix64(k ^ (unsigned long long)meta_lc(mt));
         sm.o_key[r] = k;
@@ -1389,13 +1680,24 @@ struct BeamDecoder {
     const uint32_t bnd_before = sm.bnd_count;
     const long long t_exp = stats_of(io) ? clock64() : 0;
 #endif
-    expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
+    // frames with many kept tokens go through the threshold algorithm (flat posteriors, loose
+    // token_min_logp); the common frames (K + 1 <= 4 on trained-model-like posteriors) never do
+    if constexpr (HEAVY) {
+      if (((uint32_t)sm.nkept[f] + 1u) * sm.nN[q] > kHeavyItems)
+        expand_heavy(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
+      else
+        expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
+    } else {
+      expand(sm, lm, P, sc, io, f, cur, q, nb, sc.outs_g);
+    }
     pt.mark(9);
 #if defined(__CUDA_ARCH__)
     if (stats_of(io) && threadIdx.x == 0) {  // tuning: expand time split by "frame scored a word with the LM"
       const int slot = sm.bnd_count != bnd_before ? 5 : 6;
-      sm.opc[slot] += (unsigned long long)(clock64() - t_exp);
-      sm.opn[slot] += 1u;
+      if constexpr (STATS) {
+        sm.tm.opc[slot] += (unsigned long long)(clock64() - t_exp);
+        sm.tm.opn[slot] += 1u;
+      }
     }
 #endif
     if (sm.status != 0) return;  // uniform: written before the barrier that ends expand
@@ -1469,7 +1771,9 @@ struct BeamDecoder {
           sm.cnt[5] = sm.node_count;
           sm.cnt[6] = sm.bnd_count;
           for (int k = 0; k < 8; ++k) atom_add(&stats_of(io)[k], (unsigned long long)sm.cnt[k]);
-          for (int k = 0; k < 8; ++k) { atom_add(&stats_of(io)[16 + k], sm.opc[k]); atom_add(&stats_of(io)[24 + k], (unsigned long long)sm.opn[k]); }
+          if constexpr (STATS) {
+            for (int k = 0; k < 8; ++k) { atom_add(&stats_of(io)[16 + k], sm.tm.opc[k]); atom_add(&stats_of(io)[24 + k], (unsigned long long)sm.tm.opn[k]); }
+          }
         }
       }
       for (uint32_t r = lane; r < nf && r < (uint32_t)P.n_best; r += NT) {
@@ -1561,7 +1865,8 @@ struct BeamDecoder {
       if (lane == 0 && attempt == 0) sm.is_prob = 0;
       if (lane == 0) {
         sm.status = 0;
-        for (int k = 0; k < 8; ++k) { sm.cnt[k] = 0; sm.opc[k] = 0; sm.opn[k] = 0; }
+        for (int k = 0; k < 8; ++k) sm.cnt[k] = 0;
+        if constexpr (STATS) { for (int k = 0; k < 8; ++k) { sm.tm.opc[k] = 0; sm.tm.opn[k] = 0; } }
         sm.node_count = 1;
         sm.bnd_count = 1;
         sm.nN[0] = sm.nN[1] = 0;
@@ -1590,7 +1895,7 @@ struct BeamDecoder {
           unsigned long long x = 0x6A09E667F3BCC909ULL;
           for (int k = 0; k < P.prune_history && k < kMaxCtx; ++k) x = mix64(x ^ 0ULL) + 0x9E3779B97F4A7C15ULL;
           h0.H = x;
-          sc.hist[0] = h0;
+          sc.hist()[0] = h0;
         }
         if (lm.present) {
           BndRec r0;

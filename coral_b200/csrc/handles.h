@@ -21,6 +21,7 @@ struct coral_decoder {
   const coral_lm* lm = nullptr;
   coral::HostLexicon lex;  // LM vocabulary U unigram list, with pyctcdecode's flags
   coral::LexSlot* d_lex = nullptr;
+  uint64_t* d_lex_ok = nullptr;  // per lexicon slot: tokens that extend the prefix penalty-free
   coral::DecodeParams P;   // alphabet + current alpha/beta/unk/boundary
   int device = 0;
   // scratch arenas in HBM, one set per CUDA stream the decoder is used on (launches on
@@ -31,7 +32,8 @@ struct coral_decoder {
     size_t slot_bytes = 0;
     uint32_t n_slots = 0;
     uint32_t node_cap = 0, bnd_cap = 0, ch_size = 0, outs_cap = 0, wf_cap = 0, hist_cap = 0;
-    int32_t* d_work = nullptr;
+    int32_t* d_work = nullptr;   // 4 counters + the heavy kernel's queue
+    size_t work_cap = 0;         // ints allocated at d_work
     bool budget_capped = false;  // the memory budget, not the launch, limited n_slots
   };
   std::map<void*, Scratch> scratch;

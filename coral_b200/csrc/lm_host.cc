@@ -55,6 +55,24 @@ struct Pending {
 };
 }  // namespace
 
+// Upper bound of any log10 probability BaseScore can return: the largest stored probability plus,
+// for every back-off step a query can take, the largest positive back-off weight (back-offs of a
+// pruned model may exceed 1). Used by the beam kernel's heavy-frame path to bound a word's score
+// before scoring it.
+static void compute_score_ub(HostLm& lm) {
+  float mp = -1e30f, mb = 0.0f;
+  for (size_t i = 0; i < lm.uni.size(); ++i) {
+    if (i == 0 && lm.uni[0].prob <= -99.0f) continue;  // the hallucinated <unk>
+    mp = std::max(mp, lm.uni[i].prob);
+    mb = std::max(mb, lm.uni[i].backoff);
+  }
+  for (const NgSlot& s : lm.ng)
+    if (s.key != 0) { mp = std::max(mp, s.prob); mb = std::max(mb, s.backoff); }
+  if (lm.uni.size()) mp = std::max(mp, lm.uni[0].prob);
+  if (!(mp > -1e29f)) mp = 0.0f;
+  lm.score_ub = std::max(0.0f, mp) + (float)std::max(0, lm.order - 1) * mb;
+}
+
 int load_arpa(const char* path, HostLm& lm, std::string& err) {
   FILE* f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open ARPA file: ") + path; return -2; }
@@ -203,6 +221,7 @@ int load_arpa(const char* path, HostLm& lm, std::string& err) {
     lm.ng.assign(16, NgSlot{0, 0.0f, 0.0f});
     lm.ng_mask = 15;
   }
+  compute_score_ub(lm);
   return 0;
 }
 
@@ -419,11 +438,12 @@ int load_kenlm_binary(const char* path, HostLm& lm, std::string& err) {
     }
     lm.loaded[e.n - 1]++;
   }
+  compute_score_ub(lm);
   return 0;
 }
 
 int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams, HostLexicon& out,
-                  std::string& err) {
+                  std::string& err, const std::vector<std::u32string>* labels) {
   struct Info { uint32_t wid, flags; std::u32string s; };
   std::unordered_map<uint64_t, Info> map;
   map.reserve(lm.words.size() * 6);
@@ -474,6 +494,31 @@ int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams,
     uint64_t i = (kv.first >> 20) & out.lex_mask;
     while (out.lex[i].key != 0) i = (i + 1) & out.lex_mask;
     out.lex[i] = LexSlot{kv.first, kv.second.wid, kv.second.flags};
+  }
+  out.child_ok.clear();
+  out.root_ok = 0;
+  if (labels && labels->size() <= 64) {
+    // token c extends prefix p penalty-free iff p + label(c) is a prefix of a unigram-set word
+    out.child_ok.assign(cap, 0);
+    auto slot_of = [&](uint64_t h) -> long long {
+      uint64_t i = (h >> 20) & out.lex_mask;
+      for (;;) {
+        if (out.lex[i].key == h) return (long long)i;
+        if (out.lex[i].key == 0) return -1;
+        i = (i + 1) & out.lex_mask;
+      }
+    };
+    for (const auto& kv : map) {
+      if (!(kv.second.flags & kLexPrefixOfUnigram)) continue;
+      const std::u32string& q = kv.second.s;
+      for (size_t c = 0; c < labels->size(); ++c) {
+        const std::u32string& L = (*labels)[c];
+        if (L.empty() || L.size() > q.size() || q.compare(q.size() - L.size(), L.size(), L) != 0) continue;
+        if (L.size() == q.size()) { out.root_ok |= 1ULL << c; continue; }
+        const long long sl = slot_of(hash_word(q.substr(0, q.size() - L.size())));
+        if (sl >= 0) out.child_ok[(size_t)sl] |= 1ULL << c;
+      }
+    }
   }
   return 0;
 }

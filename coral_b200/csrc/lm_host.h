@@ -27,6 +27,7 @@ struct HostLm {
   uint64_t ng_mask = 0;
   uint32_t bos_id = 0, eos_id = 0;
   int kenlm_keys = 0;  // ng holds KenLM chain keys (read from a KenLM binary), see lm_tables.h
+  float score_ub = 0.0f;  // no BaseScore result exceeds this log10 value (>= 0; see compute_score_ub)
 };
 
 struct HostLexicon {
@@ -34,6 +35,10 @@ struct HostLexicon {
   uint64_t lex_mask = 0;
   int has_unigrams = 0;
   uint64_t n_entries = 0;
+  // per slot of `lex`: alphabet tokens that extend the prefix penalty-free (see LmView::lex_ok);
+  // empty when build_lexicon was not given the alphabet
+  std::vector<uint64_t> child_ok;
+  uint64_t root_ok = 0;
 };
 
 // returns 0 on success; negative status + message otherwise
@@ -45,14 +50,15 @@ int load_kenlm_binary(const char* path, HostLm& lm, std::string& err);
 bool is_kenlm_binary(const char* path);
 
 // unigrams == nullptr <=> pyctcdecode's ``unigrams=None`` (no unigram set, no char trie)
+// labels != nullptr: also fill HostLexicon::child_ok / root_ok for that alphabet (<= 64 labels)
 int build_lexicon(const HostLm& lm, const std::vector<std::u32string>* unigrams, HostLexicon& out,
-                  std::string& err);
+                  std::string& err, const std::vector<std::u32string>* labels = nullptr);
 
 bool utf8_to_u32(const std::string& s, std::u32string& out);
 uint64_t hash_word(const std::u32string& w);
 
 inline LmView make_view(const HostLm& lm, const HostLexicon& lx, const UniEntry* uni,
-                        const NgSlot* ng, const LexSlot* lex) {
+                        const NgSlot* ng, const LexSlot* lex, const uint64_t* lex_ok = nullptr) {
   LmView v;
   v.uni = uni;
   v.ng = ng;
@@ -65,6 +71,9 @@ inline LmView make_view(const HostLm& lm, const HostLexicon& lx, const UniEntry*
   v.eos_id = lm.eos_id;
   v.has_unigrams = lx.has_unigrams;
   v.kenlm_keys = lm.kenlm_keys;
+  v.score_ub = lm.score_ub;
+  v.lex_ok = lx.child_ok.empty() ? nullptr : lex_ok;
+  v.root_ok = lx.root_ok;
   v.present = 1;
   return v;
 }

@@ -72,6 +72,11 @@ struct LmView {
   int32_t has_unigrams;  // len(unigram_set) > 0 after filtering with the LM vocabulary
   int32_t kenlm_keys;    // informational: the tables came from a KenLM binary (keys are KenLM's either way)
   int32_t present;       // 0 => decoder built without a language model
+  float score_ub;        // upper bound of any log10 probability the model returns (>= 0)
+  // heavy-frame path: per lexicon slot, the alphabet tokens whose label extends that prefix to
+  // another prefix of a unigram-set word (no partial-word penalty); NULL = not built
+  const uint64_t* lex_ok;
+  uint64_t root_ok;      // the same for the empty prefix
 };
 
 CORAL_HD uint64_t mix64(uint64_t x) {
@@ -119,6 +124,17 @@ CORAL_HD bool lex_find(const LmView& lm, uint64_t h, uint32_t& wid, uint32_t& fl
     if (key == h) { wid = s.wid; flags = s.flags; return true; }
 #endif
     if (key == 0) return false;
+    i = (i + 1) & lm.lex_mask;
+  }
+}
+
+// slot index of a prefix in the lexicon table, -1 if absent (heavy-frame path only)
+CORAL_HD long long lex_slot(const LmView& lm, uint64_t h) {
+  uint64_t i = (h >> 20) & lm.lex_mask;
+  for (;;) {
+    const uint64_t key = lm.lex[i].key;
+    if (key == h) return (long long)i;
+    if (key == 0) return -1;
     i = (i + 1) & lm.lex_mask;
   }
 }

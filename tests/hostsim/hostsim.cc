@@ -53,7 +53,10 @@ void* hs_create(const char* arpa_path, const uint32_t* label_cps, const int32_t*
       for (int64_t i = 0; i < n_uni; ++i)
         uni.emplace_back((const char32_t*)(uni_cps + uni_off[i]), (size_t)(uni_off[i + 1] - uni_off[i]));
     }
-    if (build_lexicon(d->lm, n_uni >= 0 ? &uni : nullptr, d->lx, g_err) != 0) { delete d; return nullptr; }
+    std::vector<std::u32string> labels;
+    for (int v = 0; v < n_labels; ++v)
+      labels.emplace_back((const char32_t*)(label_cps + label_off[v]), (size_t)(label_off[v + 1] - label_off[v]));
+    if (build_lexicon(d->lm, n_uni >= 0 ? &uni : nullptr, d->lx, g_err, &labels) != 0) { delete d; return nullptr; }
     d->has_lm = true;
   }
   return d;
@@ -110,18 +113,23 @@ static int run_t(HsDecoder* d, const DecodeParams& P, const float* logits, int T
   typename Dec::Sm* sm = new typename Dec::Sm();
   LmView lm;
   memset(&lm, 0, sizeof(lm));
-  if (d->has_lm) lm = make_view(d->lm, d->lx, d->lm.uni.data(), d->lm.ng.data(), d->lx.lex.data());
+  if (d->has_lm) lm = make_view(d->lm, d->lx, d->lm.uni.data(), d->lm.ng.data(), d->lx.lex.data(), d->lx.child_ok.data());
   SlotScratch sc;
   sc.node_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
   sc.bnd_cap = (uint32_t)((size_t)P.beam_width * (size_t)(T > 0 ? T : 1) + 64);
   sc.outs_cap = (uint32_t)(P.beam_width * (P.V + 1) + 64);
   std::vector<uint32_t> node_parent(sc.node_cap), node_info(sc.node_cap);
   std::vector<BndRec> bnd(sc.bnd_cap);
-  std::vector<HistRec> hist(P.prune_history ? sc.bnd_cap : 1);
-  sc.hist = hist.data();
+  sc.outs_cap = (sc.outs_cap + 3) & ~3u;
   std::vector<unsigned long long> g_key(sc.outs_cap);
   std::vector<double> g_logit(sc.outs_cap);
-  std::vector<uint32_t> g_order(sc.outs_cap), g_aux(sc.outs_cap), g_child(sc.outs_cap), g_info(sc.outs_cap);
+  // order, aux, child, info and -- addressed from info, see SlotScratch -- hv_sorted, hv_masks, history records
+  std::vector<uint32_t> g_block((size_t)sc.outs_cap * 5 + SlotScratch::kHvMaskBytes / 4 + ((sc.outs_cap + 15) & ~15u) / 4 + 4 +
+                                (P.prune_history ? (size_t)sc.bnd_cap * sizeof(HistRec) / 4 : 0));
+  uint32_t* g_order = g_block.data();
+  uint32_t* g_aux = g_order + sc.outs_cap;
+  uint32_t* g_child = g_aux + sc.outs_cap;
+  uint32_t* g_info = g_child + sc.outs_cap;
   std::vector<FrameRec> wf(FRAMES ? sc.node_cap : 1);
   sc.wf = wf.data();
   sc.wf_cap = (uint32_t)wf.size();
@@ -132,10 +140,10 @@ static int run_t(HsDecoder* d, const DecodeParams& P, const float* logits, int T
   sc.bnd = bnd.data();
   sc.outs_g.key = g_key.data();
   sc.outs_g.logit = g_logit.data();
-  sc.outs_g.order = g_order.data();
-  sc.outs_g.aux = g_aux.data();
-  sc.outs_g.child = g_child.data();
-  sc.outs_g.info = g_info.data();
+  sc.outs_g.order = g_order;
+  sc.outs_g.aux = g_aux;
+  sc.outs_g.child = g_child;
+  sc.outs_g.info = g_info;
   int32_t status = 0;
   // decode the same utterance n_utt_repeat times on the same slot: exercises slot reuse
   for (int rep = 0; rep < n_utt_repeat; ++rep) {

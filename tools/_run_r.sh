@@ -1,0 +1,9 @@
+python tools/beam_perf.py --utts 8192 --iters 5 2>&1 | grep utts
+python tools/beam_perf.py --utts 1776 --kind flat --iters 3 2>&1 | grep utts
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -4
+python bench.py --config 3 --steps 5 --warmup 3 > gpurun_out/r2_r_config3.json 2> gpurun_out/r2_r_config3.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2_r_config3.json").read().strip().splitlines()[-1])
+print({k:round(v["utt_per_s"]) for k,v in d["token_min_logp_sweep"].items()}, {k:round(v["utt_per_s"]) for k,v in d["flat_logits_128_utterances"].items()})
+PY
