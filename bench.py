@@ -499,6 +499,36 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     list_s = float(t.item())
 
+    # ---- evaluate()-shaped end to end (R:src/coral/evaluate.py:56-84): decode -> text normaliser on
+    # every transcript (numerals, lower, NFKC, conversion dict, characters_to_keep) -> cer / wer
+    from coral_b200.normalise import DEFAULT_CONVERSION_DICT, TextNormaliser
+
+    norm = TextNormaliser("abcdefghijklmnopqrstuvwxyzæøå0123456789éü", DEFAULT_CONVERSION_DICT,
+                          lower_case=True, convert_numerals=True)   # R:config/evaluation.yaml:14
+    refs_norm = norm(refs)
+
+    def step_evaluate():
+        hy = norm(dec.decode_batch(None, h_logits, beam_width=args.beam, lengths=h_len))
+        if world > 1:
+            from coral_b200.sharded import sharded_error_rates
+
+            r = sharded_error_rates(hy, refs_norm)
+            return r["cer"], r["wer"]
+        return metrics.cer(hy, refs_norm), metrics.wer(hy, refs_norm)
+
+    for _ in range(2):
+        step_evaluate()
+    barrier()
+    t0 = time.perf_counter()
+    n_eval = max(1, min(args.steps, 5))
+    for _ in range(n_eval):
+        step_evaluate()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eval_s = float(t.item())
+
     # ---- work counters (one extra untimed launch with stats)
     st = dec.decode_padded(d_logits, d_len, beam_width=args.beam, n_best=1, collect_stats=True).stats
 
@@ -588,6 +618,11 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "input": "pinned padded [B, T_max, V] host tensor + lengths (decode_batch extension)",
                     "phases_ms": phases,
+                    "evaluate_shaped": {"value": world * B * n_eval / eval_s, "unit": UNIT, "steps": n_eval,
+                                        "ms_per_step": 1e3 * eval_s / n_eval,
+                                        "path": "decode_batch -> C++ text normaliser (numerals, lower, NFKC, conversion dict, "
+                                                "characters_to_keep; host threads) -> cer/wer, as evaluate() does it "
+                                                "(R:src/coral/evaluate.py:56-84)"},
                     "list_input": {"value": world * B * n_list / list_s, "unit": UNIT, "steps": n_list,
                                    "ms_per_step": 1e3 * list_s / n_list,
                                    "input": "list of B pageable [T_i, V] numpy arrays -> decode_batch(None, list) + cer/wer "

@@ -80,7 +80,7 @@ constexpr int min_ctas() {
 // return the same beams, so its floating-point details are irrelevant. Runs in front of the lean
 // kernel (about 10 us for 8192 utterances); not used with streamed input (the frames are not
 // there yet), where everything stays with the lean kernel.
-constexpr int kHeavyKept = 12;
+constexpr int kHeavyKept = 24;
 static __global__ void __launch_bounds__(256)
 classify_heavy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ frame_off,
                       const int32_t* __restrict__ lengths, int B, int T_max, int V, float token_min_logp,
@@ -130,7 +130,8 @@ classify_heavy_kernel(const float* __restrict__ logits, const int64_t* __restric
 template <int NT, int BW, int OUTC, bool FRAMES, int MODE>
 constexpr int kernel_min_ctas() {
   constexpr int m = min_ctas<NT, BW, OUTC, FRAMES>();
-  return MODE == 2 ? (m / CORAL_HEAVY_CTA_DIV < 1 ? 1 : m / CORAL_HEAVY_CTA_DIV) : m;
+  // (only where there are thread groups to spare: the wide-beam instantiations hold 1-3 per SM)
+  return (MODE == 2 && m >= 6) ? m / CORAL_HEAVY_CTA_DIV : m;
 }
 
 template <int NT, int BW, int OUTC, bool FRAMES, bool STATS, int MODE>
