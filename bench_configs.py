@@ -223,13 +223,15 @@ def run_config4(args, rank, world, local_rank, clock_sampler):
     dev_ms = _max_over_ranks(_time_launches(torch, step_device, args.steps, args.warmup), dev, world)
     chars_ms = float(np.median([a.elapsed_time(b) for a, b in kern[-args.steps:]]))
 
+    shard_sizes = [len(shard_indices(ref_len, r, world)) for r in range(world)]
+
     def e2e():
         vs = validation_scores(hyps, refs, max_cer=0.6)
         totals = reduce_counts(vs.char_counts, vs.word_counts)
         cers, wers = rates_from_totals(totals)
         keep = torch.from_numpy(vs.keep).to(dev)
         if world > 1:  # the keep-mask of every shard, gathered (fixed-width, padded to the largest shard)
-            sizes = [len(shard_indices(ref_len, r, world)) for r in range(world)]
+            sizes = shard_sizes
             pad = torch.zeros(max(sizes), dtype=torch.bool, device=dev)
             pad[: len(keep)] = keep
             out = [torch.empty_like(pad) for _ in range(world)]

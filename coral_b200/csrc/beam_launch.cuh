@@ -90,25 +90,31 @@ classify_heavy_kernel(const float* __restrict__ logits, const int64_t* __restric
   if (u >= B) return;
   const int T = lengths[u];
   const float* base = logits + (frame_off ? (size_t)frame_off[u] : (size_t)u * T_max) * V;
-  int kept = 0, nf = 0;
-  for (int k = 0; k < 4 && k < T; ++k) {
+  // all loads first: with the logits in pinned host memory each one is a PCIe round trip
+  const int nf = T < 4 ? (T < 0 ? 0 : T) : 4;
+  float x0[4], x1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
     const int t = T <= 4 ? k : (int)(((long long)k * (T - 1)) / 3);
     const float* row = base + (size_t)t * V;
-    const float x0 = lane < V ? row[lane] : -INFINITY;
-    const float x1 = lane + 32 < V ? row[lane + 32] : -INFINITY;
-    float mx = fmaxf(x0, x1);
+    x0[k] = (k < nf && lane < V) ? row[lane] : -INFINITY;
+    x1[k] = (k < nf && lane + 32 < V) ? row[lane + 32] : -INFINITY;
+  }
+  int kept = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float mx = fmaxf(x0[k], x1[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (!isfinite(mx)) mx = 0.0f;
-    float se = (lane < V ? expf(x0 - mx) : 0.0f) + (lane + 32 < V ? expf(x1 - mx) : 0.0f);
+    float se = (lane < V ? expf(x0[k] - mx) : 0.0f) + (lane + 32 < V ? expf(x1[k] - mx) : 0.0f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     const float lse = logf(se) + mx;
-    int c = (lane < V && x0 - lse >= token_min_logp) + (lane + 32 < V && x1 - lse >= token_min_logp);
+    int c = (lane < V && x0[k] - lse >= token_min_logp) + (lane + 32 < V && x1[k] - lse >= token_min_logp);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    kept += c;
-    ++nf;
+    kept += k < nf ? c : 0;
   }
   if (lane == 0) {
     const bool heavy = nf > 0 && kept > nf * kHeavyKept;
