@@ -215,8 +215,8 @@ def test_edit_counts_capacity_is_reported_not_truncated(torch_cuda, rng):
     from oracle import edit as oe
 
     torch = torch_cuda
-    refs = ["a" * 300 + "b", "kort", "x" * 140]
-    hyps = ["a" * 290 + "c", "kart", "x" * 150]
+    refs = ["ab" * 150 + "b", "kort", "x" * 140]   # pair 0: nothing in common at either end, 301 symbols
+    hyps = ["ba" * 145 + "c", "kart", "x" * 150]
     r_cps, r_off = encode_utf32(refs)
     h_cps, h_off = encode_utf32(hyps)
     d = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
@@ -242,6 +242,67 @@ def test_edit_counts_capacity_is_reported_not_truncated(torch_cuda, rng):
     torch.cuda.synchronize()
     for sdih, status in outs:
         assert [tuple(x) for x in sdih.cpu().tolist()] == want and not status.cpu().numpy().any()
+
+
+def test_edit_counts_two_kernels_agree(torch_cuda, rng):
+    """The bit-parallel kernel and the general anti-diagonal kernel give the same counts (and both the
+    oracle's), pair by pair, in all three modes; the token 0xffffffff (the bit-parallel kernel's
+    empty-slot marker) is handed to the general kernel, not mis-scored."""
+    import subprocess, sys, json
+    from coral_b200 import metrics
+    from coral_b200.textio import encode_utf32
+    from oracle import edit as oe
+
+    torch = torch_cuda
+    refs, hyps = _random_pairs(rng, 3000, "abcdeæøå  \t", 250)
+    for k in range(0, 3000, 7):        # unrelated pairs: cores as long as the strings
+        hyps[k] = "".join(rng.choice(list("abcde æ"), size=int(rng.integers(1, 250))))
+    # every white-space code point of str.isspace() / regex \\s, and their neighbours that are not
+    spaces = [9, 10, 11, 12, 13, 28, 29, 30, 31, 32, 133, 160, 5760, 8232, 8233, 8239, 8287, 12288, *range(8192, 8203)]
+    near = [8, 14, 27, 33, 63, 64, 132, 134, 159, 161, 5759, 5761, 8191, 8203, 8231, 8234, 8238, 8240, 8286, 8288,
+            12287, 12289]
+    for k, cp in enumerate(spaces + near):
+        ch = chr(cp)
+        refs[10 + 5 * k] = f"{ch}ab{ch}cd{ch}{ch}ef g{ch} h{ch}"
+        hyps[10 + 5 * k] = f"ab cd{ch}ef  g h{ch}{ch}i"
+    got_c = metrics.edit_counts(hyps, refs, "chars")
+    got_w = metrics.edit_counts(hyps, refs, "words")
+    code = (
+        "import os, sys, json; os.environ['CORAL_B200_EDIT_NO_BITPAR'] = '1'; sys.path.insert(0, %r)\n"
+        "from coral_b200 import metrics\n"
+        "refs, hyps = json.load(sys.stdin)\n"
+        "print(json.dumps([metrics.edit_counts(hyps, refs, k).tolist() for k in ('chars', 'words')]))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], input=json.dumps([refs, hyps]), capture_output=True,
+                         text=True, check=True).stdout
+    old_c, old_w = json.loads(out.strip().splitlines()[-1])
+    assert got_c.tolist() == old_c and got_w.tolist() == old_w
+    for i in range(0, 3000, 5):
+        assert tuple(got_c[i]) == oe.char_counts(refs[i], hyps[i])
+        assert tuple(got_w[i]) == oe.word_counts(refs[i], hyps[i])
+    # tokens mode
+    n = 500
+    a = [rng.integers(0, 6, size=int(rng.integers(0, 200))).astype(np.uint32) for _ in range(n)]
+    b = [x.copy() if rng.random() < 0.5 else rng.integers(0, 6, size=int(rng.integers(0, 200))).astype(np.uint32)
+         for x in a]
+    for k in range(0, n, 3):
+        if len(a[k]):
+            a[k][rng.integers(0, len(a[k]))] = 0xFFFFFFFF
+        if len(b[k]) > 3:
+            b[k][rng.integers(0, len(b[k]))] = 0xFFFFFFFF
+            b[k] = np.delete(b[k], 1)
+    def flat(xs):
+        off = np.zeros(len(xs) + 1, np.int64)
+        off[1:] = np.cumsum([len(x) for x in xs])
+        cps = np.concatenate(xs + [np.zeros(1, np.uint32)])
+        return torch.from_numpy(cps.view(np.int32)).cuda(), torch.from_numpy(off).cuda()
+    (rc, ro), (hc, ho) = flat(a), flat(b)
+    sdih, status = metrics.edit_counts_device(rc, ro, hc, ho, n, 0, 200)
+    sdih, status = sdih.cpu().numpy(), status.cpu().numpy()
+    for i in range(n):
+        S, D, I = oe.editops_counts(a[i].tolist(), b[i].tolist())
+        assert tuple(sdih[i]) == (S, D, I, len(a[i]) - S - D), i
+        assert status[i] == (1 if len(a[i]) == 0 else 0)
 
 
 def test_get_score_df_and_validation(torch_cuda, rng):
