@@ -574,11 +574,17 @@ class BeamSearchDecoderCTC:
         arrays, or (extension) a padded ``[B, T_max, V]`` array/tensor with ``lengths``."""
         if hotwords:
             raise NotImplementedError("hotwords are not implemented (never passed by CoRal; SURVEY.md 8 A9)")
+        launched = self._batch_launch(logits_list, lengths, beam_width, beam_prune_logp, token_min_logp)
+        return [] if launched is None else self._batch_finish(launched)
+
+    def _batch_launch(self, logits_list, lengths, beam_width, beam_prune_logp, token_min_logp):
+        """Queue one batch on the current stream: decode + transcripts as UTF-32 on the device. Returns the
+        device tensors (and what must stay alive until the launch has run), or None for an empty list."""
         torch = _torch()
         if lengths is None:
             logits_list = list(logits_list)
             if not logits_list:
-                return []
+                return None
             if not 1 <= beam_width <= MAX_BEAM_WIDTH:
                 raise ValueError(f"beam_width must be in [1, {MAX_BEAM_WIDTH}]")
             self._handle()
@@ -590,14 +596,73 @@ class BeamSearchDecoderCTC:
         else:
             d_n, d_logit, d_comb, d_tok, d_lens, d_status, _ = self.decode_padded(
                 logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1, to_host=False)
-        d_text = self.device_text(d_tok, d_lens)
+            keep = (getattr(self, "_keepalive", None), logits_list, lengths)  # inputs outlive the launch
+        return (*self.device_text(d_tok, d_lens), d_status, keep)
+
+    def _batch_finish(self, launched) -> "DecodedTexts":
+        d_cps, d_off, d_max, d_status, _keep = launched
         # one small read-back tells whether any utterance ran out of arena capacity
         bad_any = int(d_status.abs().max().item()) if d_status.numel() else 0
         if bad_any:
             status = d_status.cpu().numpy()
             bad = np.nonzero(status)[0]
             raise _lib.CoralError(int(status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
-        return self._texts_from_device(*d_text)
+        return self._texts_from_device(d_cps, d_off, d_max)
+
+    def decode_batches(self, batches, beam_width: int = DEFAULT_BEAM_WIDTH,
+                       beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                       prefetch: int = 1):
+        """(extension) ``decode_batch`` over an iterable of batches, one batch ahead: yields the
+        transcripts of batch k while batch k + 1 is already decoding, so the caller's host work on
+        batch k (strings, ``cer`` / ``wer``, bookkeeping) overlaps the next decode -- the loop
+        ``for batch in dataloader: decode; score`` of R:src/coral/evaluate.py / validation.py.
+
+        Every item of ``batches`` is either a list of ``[T_i, V]`` arrays or a ``(padded logits,
+        lengths)`` pair, as ``decode_batch`` takes them. The decodes are queued on a stream this
+        decoder owns; the stream that is current when a batch is yielded waits for exactly that batch,
+        so work the caller queues (the metric kernels) is not held up behind the next decode.
+        Results and their order are those of calling ``decode_batch`` batch by batch."""
+        import collections
+
+        torch = _torch()
+        self._handle()
+        dev = torch.device("cuda", self._device)
+        if getattr(self, "_pipe_stream", None) is None:
+            self._pipe_stream = torch.cuda.Stream(device=dev)
+        pipe = self._pipe_stream
+        it = iter(batches)
+        pending = collections.deque()
+
+        def launch():
+            try:
+                batch = next(it)
+            except StopIteration:
+                return False
+            logits, lengths = batch if isinstance(batch, tuple) and len(batch) == 2 else (batch, None)
+            pipe.wait_stream(torch.cuda.current_stream(dev))  # inputs produced on the caller's stream
+            with torch.cuda.stream(pipe):
+                launched = self._batch_launch(logits, lengths, beam_width, beam_prune_logp, token_min_logp)
+                done = torch.cuda.Event()
+                done.record(pipe)
+            pending.append((launched, done))
+            return True
+
+        more = True
+        depth = 1 + max(0, int(prefetch))
+        while True:
+            while more and len(pending) < depth:
+                more = launch()
+            if not pending:
+                break
+            launched, done = pending.popleft()
+            if launched is None:
+                yield []
+                continue
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(done)
+            for t in launched[:4]:
+                t.record_stream(cur)  # allocated on the decoder's stream, consumed on the caller's
+            yield self._batch_finish(launched)
 
     # ------------------------------------------------------------- serialisation
     def save_to_dir(self, filepath: str) -> None:

@@ -584,6 +584,43 @@ def test_streamed_host_input_equals_resident_input(gpu_decoder, oracle_decoder, 
         beams_equal(oracle_decoder.decode_beams(x), g)
 
 
+def test_decode_batches_one_ahead_equals_batch_by_batch(gpu_decoder, torch_cuda, cache_dir, rng):
+    """decode_batches (the next batch decoding while the caller scores this one) yields what
+    decode_batch returns batch by batch, in order, for every input form; the yielded lists carry
+    their device text, and cer()/wer() queued by the caller between batches are right."""
+    import synth
+    from coral_b200 import metrics
+    from oracle import edit as oe
+
+    torch = torch_cuda
+    w = synth.build_workload(cache_dir, 256, order=4, n_words=2000, n_sent=5000, name="big")
+    idxs = [rng.permutation(256)[: int(n)] for n in (200, 1, 64, 256, 17)]
+    want = [list(gpu_decoder.decode_batch(None, torch.from_numpy(w.logits[i]).cuda(), lengths=w.lengths[i]))
+            for i in idxs]
+
+    def forms():
+        for k, i in enumerate(idxs):
+            if k % 3 == 0:
+                yield (torch.from_numpy(w.logits[i]).pin_memory(), w.lengths[i])        # pinned: read in place
+            elif k % 3 == 1:
+                yield [w.logits[u, : w.lengths[u]] for u in i]                           # list of [T_i, V] arrays
+            else:
+                yield (torch.from_numpy(w.logits[i]).cuda(), torch.from_numpy(w.lengths[i]))  # device resident
+
+    for prefetch in (1, 0, 3):
+        seen = 0
+        for k, got in enumerate(gpu_decoder.decode_batches(forms(), prefetch=prefetch)):
+            assert list(got) == want[k], (prefetch, k)
+            refs = [w.references[u] for u in idxs[k]]
+            assert getattr(got, "_coral_dev", None) is not None
+            assert metrics.cer(got, refs) == oe.cer(want[k], refs) and metrics.wer(got, refs) == oe.wer(want[k], refs)
+            seen += 1
+        assert seen == len(idxs)
+    assert list(gpu_decoder.decode_batches([])) == []
+    assert [list(x) for x in gpu_decoder.decode_batches([[], [w.logits[3, : w.lengths[3]]]])] == \
+        [[], list(gpu_decoder.decode_batch(None, [w.logits[3, : w.lengths[3]]]))]
+
+
 def test_host_inputs_are_read_in_place_and_packed_ragged(gpu_decoder, torch_cuda, cache_dir, rng):
     """Host logits never get a staging copy on the device: a pinned padded tensor is read in place
     by the kernel, pageable arrays (a padded array, or the list of [T_i, V] arrays HF hands over)
