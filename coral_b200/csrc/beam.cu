@@ -15,6 +15,20 @@
 
 using namespace coral;
 
+// threads per utterance of the two wide-beam instantiations (tuning: profiles/r2_beam_kernel_tuning.md)
+#ifndef CORAL_NT_BEAM256
+#define CORAL_NT_BEAM256 256
+#endif
+#ifndef CORAL_NT_BEAM512
+#define CORAL_NT_BEAM512 512
+#endif
+#ifndef CORAL_OUTC_BEAM256
+#define CORAL_OUTC_BEAM256 640
+#endif
+#ifndef CORAL_OUTC_BEAM512
+#define CORAL_OUTC_BEAM512 1280
+#endif
+
 extern "C" {
 
 int32_t coral_decoder_create(const uint32_t* label_cps, const int32_t* label_offsets, int32_t n_labels,
@@ -203,8 +217,8 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   // Resident groups per SM 4 / 5 / 6 / 7 / 8: 22.4 / 19.0 / 17.1 / 15.5 / 15.1 ms per 8192 utterances
   if (beam_width <= 104) return launch_beam<128, 104, 208>(dec, L, B, st);
   if (beam_width <= 128) return launch_beam<128, 128, 320>(dec, L, B, st);
-  if (beam_width <= 256) return launch_beam<256, 256, 640>(dec, L, B, st);
-  return launch_beam<256, 512, 1280>(dec, L, B, st);
+  if (beam_width <= 256) return launch_beam<CORAL_NT_BEAM256, 256, CORAL_OUTC_BEAM256>(dec, L, B, st);
+  return launch_beam<CORAL_NT_BEAM512, 512, CORAL_OUTC_BEAM512>(dec, L, B, st);
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ d = torch.from_numpy(wl.logits).cuda(); l = torch.from_numpy(wl.lengths).cuda()
 for _ in range(5): greedy_decode_device(d, l, blank_id=45)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:edit_counts_kernel -s 4 -c 1 -o gpurun_out/final/r2_edit python tools/validation_perf.py 200000 > gpurun_out/final/ncu_edit.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:edit_bitpar -s 2 -c 1 -o gpurun_out/final/r2_edit python tools/validation_perf.py 200000 > gpurun_out/final/ncu_edit.log 2>&1
 python tools/validation_perf.py 200000 > gpurun_out/final/r2_validation_perf.json 2>&1
 python tools/greedy_perf.py > gpurun_out/final/r2_greedy_roofline.jsonl 2>&1
 ls -la gpurun_out/final
