@@ -440,13 +440,14 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the same steps through decode_batches: batch k + 1 is decoding while the host turns batch k
     # into strings and scores it (the dataset loop of evaluate() / add_validations)
-    def score(hy):
+    def score(hy, labels=None):
+        labels = refs if labels is None else labels
         if world > 1:
             from coral_b200.sharded import sharded_error_rates
 
-            r = sharded_error_rates(hy, refs)
+            r = sharded_error_rates(hy, labels)
             return r["cer"], r["wer"]
-        return metrics.cer(hy, refs), metrics.wer(hy, refs)
+        return metrics.cer(hy, labels), metrics.wer(hy, labels)
 
     def run_pipelined(n):
         last = None
@@ -512,22 +513,29 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(2):
         hy = dec.decode_batch(None, lst, beam_width=args.beam)
     assert list(hy) == list(hyps)
-    barrier()
-    t0 = time.perf_counter()
     n_list = max(1, min(args.steps, 5))
-    for _ in range(n_list):
-        hy = dec.decode_batch(None, lst, beam_width=args.beam)
-        if world > 1:
-            from coral_b200.sharded import sharded_error_rates
 
-            sharded_error_rates(hy, refs)
-        else:
-            metrics.cer(hy, refs), metrics.wer(hy, refs)
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    list_s = float(t.item())
+    def timed_host(fn):
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def list_one_at_a_time():
+        for _ in range(n_list):
+            score(dec.decode_batch(None, lst, beam_width=args.beam))
+
+    def list_pipelined(n=n_list):
+        for hy in dec.decode_batches((lst for _ in range(n)), beam_width=args.beam):
+            score(hy)
+
+    list_s = timed_host(list_one_at_a_time)
+    list_pipelined(2)
+    list_pipe_s = timed_host(list_pipelined)
 
     # ---- evaluate()-shaped end to end (R:src/coral/evaluate.py:56-84): decode -> text normaliser on
     # every transcript (numerals, lower, NFKC, conversion dict, characters_to_keep) -> cer / wer
@@ -548,16 +556,19 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(2):
         step_evaluate()
-    barrier()
-    t0 = time.perf_counter()
     n_eval = max(1, min(args.steps, 5))
-    for _ in range(n_eval):
-        step_evaluate()
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    eval_s = float(t.item())
+
+    def eval_one_at_a_time():
+        for _ in range(n_eval):
+            step_evaluate()
+
+    def eval_pipelined(n=n_eval):
+        for hy in dec.decode_batches(((h_logits, h_len) for _ in range(n)), beam_width=args.beam):
+            score(norm(hy), refs_norm)
+
+    eval_s = timed_host(eval_one_at_a_time)
+    eval_pipelined(2)
+    eval_pipe_s = timed_host(eval_pipelined)
 
     # ---- work counters (one extra untimed launch with stats)
     st = dec.decode_padded(d_logits, d_len, beam_width=args.beam, n_best=1, collect_stats=True).stats
@@ -655,13 +666,15 @@ def run_ours(args, rank, world, local_rank):
                                            "api": "hyps = decoder.decode_batch(None, logits, lengths=...); cer(hyps, refs); "
                                                   "wer(hyps, refs) -- nothing overlapped across steps"},
                     "phases_ms": phases,
-                    "evaluate_shaped": {"value": world * B * n_eval / eval_s, "unit": UNIT, "steps": n_eval,
-                                        "ms_per_step": 1e3 * eval_s / n_eval,
+                    "evaluate_shaped": {"value": world * B * n_eval / eval_pipe_s, "unit": UNIT, "steps": n_eval,
+                                        "ms_per_step": 1e3 * eval_pipe_s / n_eval,
+                                        "one_call_at_a_time": world * B * n_eval / eval_s,
                                         "path": "decode_batch -> C++ text normaliser (numerals, lower, NFKC, conversion dict, "
                                                 "characters_to_keep; host threads) -> cer/wer, as evaluate() does it "
                                                 "(R:src/coral/evaluate.py:56-84)"},
-                    "list_input": {"value": world * B * n_list / list_s, "unit": UNIT, "steps": n_list,
-                                   "ms_per_step": 1e3 * list_s / n_list,
+                    "list_input": {"value": world * B * n_list / list_pipe_s, "unit": UNIT, "steps": n_list,
+                                   "ms_per_step": 1e3 * list_pipe_s / n_list,
+                                   "one_call_at_a_time": world * B * n_list / list_s,
                                    "input": "list of B pageable [T_i, V] numpy arrays -> decode_batch(None, list) + cer/wer "
                                             "(the call shape of HF Wav2Vec2ProcessorWithLM.batch_decode -> decode_beams_batch)"}},
             "gpu_launches": 8 * args.steps,

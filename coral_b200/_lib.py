@@ -36,6 +36,7 @@ SIGNATURES = {
     "coral_decoder_tokens_to_text": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "coral_host_pack_rows": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32]),
     "coral_py_string_list": (C.py_object, [_vp, _i32, _vp, _i64]),
+    "coral_py_logits_rows": (_i64, [C.py_object, _i32, _vp, _vp, _vp]),
     "coral_normaliser_create": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, C.POINTER(_vp)]),
     "coral_normaliser_free": (_i32, [_vp]),
     "coral_normaliser_run": (_i32, [_vp, _vp, _vp, _i64, _i32, C.POINTER(_i64)]),
@@ -75,10 +76,12 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    # the one entry point that calls back into CPython must run with the GIL held
-    pyfn = C.PyDLL(path).coral_py_string_list
-    pyfn.restype, pyfn.argtypes = SIGNATURES["coral_py_string_list"]
-    lib.coral_py_string_list = pyfn
+    # the entry points that call back into CPython must run with the GIL held
+    pydll = C.PyDLL(path)
+    for name in ("coral_py_string_list", "coral_py_logits_rows"):
+        pyfn = getattr(pydll, name)
+        pyfn.restype, pyfn.argtypes = SIGNATURES[name]
+        setattr(lib, name, pyfn)
     _lib = lib
     return lib
 

@@ -22,11 +22,14 @@ using namespace coral;
 #ifndef CORAL_NT_BEAM512
 #define CORAL_NT_BEAM512 512
 #endif
+#ifndef CORAL_OUTC_BEAM128
+#define CORAL_OUTC_BEAM128 320
+#endif
 #ifndef CORAL_OUTC_BEAM256
-#define CORAL_OUTC_BEAM256 640
+#define CORAL_OUTC_BEAM256 416
 #endif
 #ifndef CORAL_OUTC_BEAM512
-#define CORAL_OUTC_BEAM512 1280
+#define CORAL_OUTC_BEAM512 1024
 #endif
 
 extern "C" {
@@ -216,7 +219,7 @@ int32_t coral_ctc_beam_decode(coral_decoder* dec, const float* logits_dev, const
   // on an SM (28 KB of shared memory, 64 registers) against the 128-beam instantiation's six.
   // Resident groups per SM 4 / 5 / 6 / 7 / 8: 22.4 / 19.0 / 17.1 / 15.5 / 15.1 ms per 8192 utterances
   if (beam_width <= 104) return launch_beam<128, 104, 208>(dec, L, B, st);
-  if (beam_width <= 128) return launch_beam<128, 128, 320>(dec, L, B, st);
+  if (beam_width <= 128) return launch_beam<128, 128, CORAL_OUTC_BEAM128>(dec, L, B, st);
   if (beam_width <= 256) return launch_beam<CORAL_NT_BEAM256, 256, CORAL_OUTC_BEAM256>(dec, L, B, st);
   return launch_beam<CORAL_NT_BEAM512, 512, CORAL_OUTC_BEAM512>(dec, L, B, st);
 }

@@ -199,4 +199,60 @@ void* coral_py_string_list(const void* data, int32_t kind, const int64_t* offset
   return list;
 }
 
+// Py_buffer as CPython 3.x lays it out (Include/pybuffer.h / object.h; unchanged since 3.0)
+struct CoralPyBuffer {
+  void* buf;
+  void* obj;
+  ssize_t len;
+  ssize_t itemsize;
+  int readonly;
+  int ndim;
+  char* format;
+  ssize_t* shape;
+  ssize_t* strides;
+  ssize_t* suboffsets;
+  void* internal;
+};
+
+int64_t coral_py_logits_rows(void* list, int32_t V, int64_t* out_ptrs, int64_t* out_frames, uint8_t* out_other) {
+  typedef ssize_t (*list_size_t)(void*);
+  typedef void* (*list_get_t)(void*, ssize_t);
+  typedef int (*get_buffer_t)(void*, CoralPyBuffer*, int);
+  typedef void (*release_t)(CoralPyBuffer*);
+  typedef void (*err_clear_t)(void);
+  typedef int (*list_check_t)(void*);
+  static list_size_t list_size = (list_size_t)dlsym(RTLD_DEFAULT, "PyList_Size");
+  static list_get_t list_get = (list_get_t)dlsym(RTLD_DEFAULT, "PyList_GetItem");
+  static get_buffer_t get_buffer = (get_buffer_t)dlsym(RTLD_DEFAULT, "PyObject_GetBuffer");
+  static release_t release = (release_t)dlsym(RTLD_DEFAULT, "PyBuffer_Release");
+  static err_clear_t err_clear = (err_clear_t)dlsym(RTLD_DEFAULT, "PyErr_Clear");
+  if (!list_size || !list_get || !get_buffer || !release || !err_clear || !list || !out_ptrs || !out_frames ||
+      !out_other || V <= 0)
+    return -1;
+  const ssize_t n = list_size(list);
+  if (n < 0) { err_clear(); return -1; }
+  constexpr int kStridesFormat = 0x0008 | 0x0010 | 0x0004;  // PyBUF_STRIDES (incl. PyBUF_ND) | PyBUF_FORMAT
+  for (ssize_t i = 0; i < n; ++i) {
+    void* item = list_get(list, i);  // borrowed
+    CoralPyBuffer view;
+    bool ok = false;
+    if (item && get_buffer(item, &view, kStridesFormat) == 0) {
+      const char* f = view.format ? view.format : "";
+      if (*f == '<' || *f == '=' || *f == '@') ++f;
+      ok = view.ndim == 2 && view.itemsize == 4 && f[0] == 'f' && f[1] == 0 && view.shape && view.strides &&
+           view.shape[1] == V && (view.shape[0] == 0 || (view.strides[1] == 4 && (view.shape[0] == 1 || view.strides[0] == 4 * (ssize_t)V)));
+      if (ok) {
+        out_ptrs[i] = (int64_t)(intptr_t)view.buf;
+        out_frames[i] = (int64_t)view.shape[0];
+      }
+      release(&view);
+    } else {
+      err_clear();
+    }
+    out_other[i] = ok ? 0 : 1;
+    if (!ok) { out_ptrs[i] = 0; out_frames[i] = 0; }
+  }
+  return (int64_t)n;
+}
+
 }  // extern "C"

@@ -358,17 +358,23 @@ class BeamSearchDecoderCTC:
 
     # ------------------------------------------------------------ host rows -> ragged pinned buffer
     def _staging(self, n_floats: int):
-        """Pinned staging buffer (grown geometrically, reused call after call). A launch that may
-        still be reading it is waited for before it is overwritten."""
+        """Pinned staging buffer of the next slot (two slots alternate, so that one batch can be packed
+        while the launch of the previous one still reads its own; grown geometrically, reused call
+        after call). The launch that last read this slot is waited for before it is overwritten.
+        Returns (buffer, slot)."""
         torch = _torch()
-        ev = getattr(self, "_staging_event", None)
-        if ev is not None:
-            ev.synchronize()
-            self._staging_event = None
-        buf = getattr(self, "_pinned", None)
-        if buf is None or buf.numel() < n_floats:
-            self._pinned = buf = torch.empty(max(n_floats, 1 << 16) * 5 // 4, dtype=torch.float32, pin_memory=True)
-        return buf
+        if getattr(self, "_stage", None) is None:
+            self._stage = [{"buf": None, "event": None, "ready": None} for _ in range(2)]
+            self._stage_next = 0
+        slot = self._stage_next
+        self._stage_next = 1 - slot
+        st = self._stage[slot]
+        if st["event"] is not None:
+            st["event"].synchronize()
+            st["event"] = None
+        if st["buf"] is None or st["buf"].numel() < n_floats:
+            st["buf"] = torch.empty(max(n_floats, 1 << 16) * 5 // 4, dtype=torch.float32, pin_memory=True)
+        return st["buf"], slot
 
     def _decode_rows(self, ptrs, lens_np, T_pitch, dev, beam_width, beam_prune_logp, token_min_logp, n_best,
                      input_mode, d_stats, word_frames, prune_history):
@@ -384,7 +390,7 @@ class BeamSearchDecoderCTC:
         row_bytes = V * 4
         off = np.zeros(B + 1, dtype=np.int64)
         np.cumsum(lens_np, out=off[1:])
-        stage = self._staging(int(off[-1]) * V)
+        stage, slot = self._staging(int(off[-1]) * V)
         dst_off = off[:-1] * row_bytes
         nbytes = lens_np * row_bytes
         ptrs = np.ascontiguousarray(ptrs, dtype=np.int64)
@@ -401,9 +407,9 @@ class BeamSearchDecoderCTC:
                                    token_min_logp, n_best, input_mode, d_stats, word_frames=word_frames,
                                    prune_history=prune_history, d_frame_off=d_foff)
         else:
-            if getattr(self, "_ready_host", None) is None:
-                self._ready_host = torch.zeros(16, dtype=torch.int32).pin_memory()
-            ready = self._ready_host
+            if self._stage[slot]["ready"] is None:
+                self._stage[slot]["ready"] = torch.zeros(16, dtype=torch.int32).pin_memory()
+            ready = self._stage[slot]["ready"]
             ready_np = ready.numpy()
             ready_np[0] = 0
             chunk_id = np.arange(B, dtype=np.int64) // H2D_CHUNK
@@ -422,8 +428,8 @@ class BeamSearchDecoderCTC:
                 _lib.check(lib.coral_host_pack_rows(ptrs[a0:].ctypes.data, nbytes[a0:].ctypes.data,
                                                     dst_off[a0:].ctypes.data, b0 - a0, stage.data_ptr(), nthr))
                 ready_np[0] = b0  # x86 keeps stores in order: the rows are visible before the counter
-        self._staging_event = torch.cuda.Event()
-        self._staging_event.record(torch.cuda.current_stream(dev))
+        self._stage[slot]["event"] = torch.cuda.Event()
+        self._stage[slot]["event"].record(torch.cuda.current_stream(dev))
         return out
 
     def device_text(self, d_tok, d_lens):
@@ -485,19 +491,30 @@ class BeamSearchDecoderCTC:
         return ["".join(labels[t] for t in flat[off[i] : off[i + 1]]) for i in range(N)]
 
     def _rows(self, logits_list):
-        """list of ``[T_i, V]`` arrays -> (row pointers int64 [B], frames int64 [B], keep-alive list)."""
+        """list of ``[T_i, V]`` arrays -> (row pointers int64 [B], frames int64 [B], keep-alive list).
+        One C loop over the list reads every float32 C-contiguous array through the buffer protocol
+        (``coral_py_logits_rows``); only what it does not recognise goes through numpy here."""
         V = len(self._idx2vocab)
-        keep = []
-        for lg in logits_list:
-            if not isinstance(lg, np.ndarray):
-                lg = np.asarray(lg)
-            self._check_logits_dimension(lg)
-            if lg.dtype != np.float32 or not lg.flags.c_contiguous:
-                lg = np.ascontiguousarray(lg, dtype=np.float32)
-            keep.append(lg)
+        keep = logits_list if isinstance(logits_list, list) else list(logits_list)
         B = len(keep)
-        ptrs = np.fromiter((a.ctypes.data for a in keep), dtype=np.int64, count=B)
-        lens = np.fromiter((a.shape[0] for a in keep), dtype=np.int64, count=B)
+        ptrs = np.empty(B, dtype=np.int64)
+        lens = np.empty(B, dtype=np.int64)
+        other = np.empty(B, dtype=np.uint8)
+        if _lib.load().coral_py_logits_rows(keep, V, ptrs.ctypes.data, lens.ctypes.data, other.ctypes.data) != B:
+            raise RuntimeError("coral_py_logits_rows failed")
+        rest = np.nonzero(other)[0]
+        if len(rest):
+            keep = list(keep)
+            for i in rest.tolist():
+                lg = keep[i]
+                if not isinstance(lg, np.ndarray):
+                    lg = np.asarray(lg)
+                self._check_logits_dimension(lg)
+                if lg.dtype != np.float32 or not lg.flags.c_contiguous:
+                    lg = np.ascontiguousarray(lg, dtype=np.float32)
+                keep[i] = lg
+                ptrs[i] = lg.ctypes.data
+                lens[i] = lg.shape[0]
         return ptrs, lens, keep
 
     # ---------------------------------------------------- pyctcdecode's public API

@@ -179,6 +179,15 @@ int32_t coral_host_pack_rows(const void* const* src, const int64_t* n_bytes, con
  * Returns a PyObject* (new reference) or NULL. */
 void* coral_py_string_list(const void* data, int32_t kind, const int64_t* offsets, int64_t n);
 
+/* HOST helper for Python hosts: the row pointers of a Python list of [T_i, V] float32 C-contiguous
+ * buffers (numpy arrays) -- what Wav2Vec2ProcessorWithLM.batch_decode passes to decode_beams_batch
+ * (HF:models/wav2vec2_with_lm/processing_wav2vec2_with_lm.py:371, :398-406) -- read through the buffer
+ * protocol in one C loop instead of a Python loop over 8192 arrays. out_ptrs / out_frames [n] get the
+ * data address and T_i of every conforming item; out_other[i] = 1 marks an item the caller must convert
+ * itself (not a buffer, wrong dtype / rank / width, not contiguous). The list keeps the arrays alive;
+ * nothing is retained. Returns n, or -1. Call with the GIL held (ctypes.PyDLL). */
+int64_t coral_py_logits_rows(void* list, int32_t V, int64_t* out_ptrs, int64_t* out_frames, uint8_t* out_other);
+
 /* -------------------------------------------------------------------- greedy (A3/A4) */
 
 /* np.argmax(axis=-1) + Wav2Vec2CTCTokenizer grouping (R:src/coral/compute_metrics.py:62-70;

@@ -192,3 +192,49 @@ def test_host_pack_rows_packs_ragged_rows_with_threads():
         assert np.array_equal(dst, np.concatenate(rows, axis=0))
     with pytest.raises(ValueError):
         _lib.check(lib.coral_host_pack_rows(None, None, None, 3, None, 1))
+
+
+def test_py_logits_rows_reads_the_list_through_the_buffer_protocol():
+    """coral_py_logits_rows: addresses and frame counts of float32 C-contiguous [T_i, V] arrays in one C
+    loop; everything else (other dtypes, views with strides, wrong width or rank, non-buffers) is marked
+    for the caller, and BeamSearchDecoderCTC._rows converts exactly those."""
+    import torch
+
+    from coral_b200 import _lib
+    from coral_b200.decoder import build_ctcdecoder
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    V = 46
+    big = rng.standard_normal((9, 50, V)).astype(np.float32)
+    items = [
+        big[0, :17],                                         # view, contiguous rows
+        np.zeros((0, V), np.float32),                        # empty utterance
+        big[1, :1],                                          # one frame
+        big[2, ::2],                                         # strided rows        -> other
+        big[3, :20].astype(np.float64),                      # wrong dtype         -> other
+        np.asfortranarray(big[4, :20]),                      # column-major        -> other
+        big[5, :20, :45],                                    # wrong width         -> other
+        big[6, :20].tolist(),                                # not a buffer        -> other
+        torch.from_numpy(big[7, :9]).numpy(),                # round trip through torch
+        big[8].reshape(-1),                                  # wrong rank          -> other
+    ]
+    n = len(items)
+    ptrs, lens, other = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.uint8)
+    assert lib.coral_py_logits_rows(items, V, ptrs.ctypes.data, lens.ctypes.data, other.ctypes.data) == n
+    assert other.tolist() == [0, 0, 0, 1, 1, 1, 1, 1, 0, 1]
+    for i in np.nonzero(other == 0)[0]:
+        assert lens[i] == items[i].shape[0]
+        assert lens[i] == 0 or ptrs[i] == items[i].ctypes.data
+    assert lib.coral_py_logits_rows([], V, ptrs.ctypes.data, lens.ctypes.data, other.ctypes.data) == 0
+
+    labels = [chr(ord("a") + i) for i in range(26)] + list("0123456789") + list(" åæéøü") + ["<s>", "</s>", "<unk>", "<pad>"]
+    dec = build_ctcdecoder(labels)
+    good = [it for k, it in enumerate(items) if k not in (6, 9)]   # wrong width / rank raise, as pyctcdecode does
+    p2, l2, keep = dec._rows(good)
+    for a, p, l in zip(keep, p2, l2):
+        assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous
+        assert l == a.shape[0] and (l == 0 or p == a.ctypes.data)
+    assert np.array_equal(keep[3], big[2, ::2]) and np.array_equal(keep[4], big[3, :20])
+    with pytest.raises(ValueError):
+        dec._rows([items[6]])
