@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(NT, kernel_min_ctas<NT, BW, OUTC, FRAMES, MODE
     if (threadIdx.x == 0) sm.utt = atomicAdd(L.work + (MODE == 2 ? 3 : 0), 1);
     group_sync<NT>();
     const int i = sm.utt;
+    group_sync<NT>();  // the skips below loop straight back to the next claim: everyone has read this one
     if (i >= L.B) break;
     const int u = L.order ? L.order[i] : i;
     // many kept tokens per frame (flat posteriors, a loose token_min_logp): that utterance belongs to
