@@ -363,7 +363,7 @@ __device__ int split_words_bits(const uint32_t* raw, int n, int lane, uint32_t* 
 //      ahead and are parked in shared memory, so that everything below runs without a global-memory
 //      round trip: strip, (words: split, canonical word ids), common affixes, and the pattern-match
 //      word PM[j][w] of every hypothesis symbol j through a 128-slot hash of pattern word w.
-//   B  (lane = pair) the recurrence, 64 cells per word operation, PM rows prefetched four ahead;
+//   B  (lane = pair) the recurrence, 64 cells per word operation, PM words of four rows per load;
 //      VP / VN of every row go to the warp's [row][word][lane] area in HBM (coalesced).
 //   C  (lane = pair) the backtrace over a register window of eight rows per memory round trip.
 
@@ -404,7 +404,10 @@ edit_bitpar_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
   Sh& sh = s_all[warp];
   const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
   const int64_t nwarps = (int64_t)gridDim.x * WARPS;
-  ulonglong2* rows = area + (size_t)gw * ((size_t)CAP * NW * 32);  // [row][word][lane]
+  // per warp: VP / VN rows [row][word][lane] (16 B per lane: coalesced in phase B), then the pattern-match
+  // words [pair][word][row] (8 B: a pair's rows are consecutive, so phase A writes whole sectors)
+  ulonglong2* rows = area + (size_t)gw * ((size_t)CAP * NW * 48);
+  unsigned long long* pmw = reinterpret_cast<unsigned long long*>(rows + (size_t)CAP * NW * 32);
   uint32_t* key = sh.key;
   uint32_t* mask = sh.mask;
   for (int i = lane; i < kHashSlots; i += 32) { key[i] = kEmptyKey; mask[2 * i] = 0; mask[2 * i + 1] = 0; }
@@ -578,7 +581,7 @@ edit_bitpar_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
                 h = (h + 1) & (kHashSlots - 1);
               }
             }
-            rows[((size_t)j * NW + w) * 32 + q].x = pm;
+            pmw[((size_t)q * NW + w) * CAP + j] = pm;
           }
           __syncwarp();
 #pragma unroll
@@ -607,13 +610,23 @@ edit_bitpar_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
       int dist = my_m1;
       const unsigned long long last = 1ull << ((my_m1 - 1) & 63);
       constexpr int PF = NW <= 2 ? 4 : 2;
+      const unsigned long long* pml = pmw + (size_t)lane * NW * CAP;
       for (int j0 = 0; j0 < my_m2; j0 += PF) {
-        unsigned long long pm[PF][NW];
+        unsigned long long pm[PF][NW];  // PF consecutive rows of a word: 16-byte loads (rows past m2 are unused)
 #pragma unroll
-        for (int t = 0; t < PF; ++t)
+        for (int w = 0; w < NW; ++w) {
+          if (w < nw) {
 #pragma unroll
-          for (int w = 0; w < NW; ++w)
-            pm[t][w] = (j0 + t < my_m2 && w < nw) ? rows[((size_t)(j0 + t) * NW + w) * 32 + lane].x : 0ull;
+            for (int t = 0; t < PF; t += 2) {
+              const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pml + (size_t)w * CAP + j0 + t);
+              pm[t][w] = v.x;
+              pm[t + 1][w] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < PF; ++t) pm[t][w] = 0ull;
+          }
+        }
 #pragma unroll
         for (int t = 0; t < PF; ++t) {
           if (j0 + t < my_m2) {
@@ -720,7 +733,7 @@ static int32_t launch_bitpar(const uint32_t* ref_cps, const int64_t* ref_beg, co
   const int sms = sm_count(device);
   const int64_t tiles = (n_pairs + 31) / 32;
   const unsigned grid = (unsigned)std::min<int64_t>((tiles + 3) / 4, (int64_t)sms * MIN_CTAS);
-  const size_t per_warp = (size_t)(64 * NW) * NW * 32 * sizeof(ulonglong2);
+  const size_t per_warp = (size_t)(64 * NW) * NW * 48 * sizeof(ulonglong2);  // VP / VN rows + pattern-match words
   uint8_t* area = nullptr;
   const int32_t rc = edit_area(device, st, 1, per_warp * 4 * grid, &area);
   if (rc != CORAL_OK) return rc;
