@@ -605,8 +605,8 @@ def run_ours(args, rank, world, local_rank):
             "ctc_greedy (argmax + collapse)": {
                 "ms": g_ms, "algorithmic_bytes": g_bytes, "GB_per_s": g_bytes / g_ms / 1e6, "bound": "hbm",
                 "note": "greedy decode of the same ragged logits (configs[0] / config 4 path); inputs 425 MB > L2"},
-            "edit_counts_kernel(chars)": {
-                "ms": e_ms, "cells": cells, "GCUPS": cells / e_ms / 1e6, "bound": "integer ALU / shared memory"},
+            "edit_bitpar_kernel(chars)": {
+                "ms": e_ms, "cells": cells, "GCUPS": cells / e_ms / 1e6, "bound": "integer ALU (bit-parallel recurrence), memory latency"},
         }
 
     if rank == 0:

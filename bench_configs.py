@@ -270,10 +270,10 @@ def run_config4(args, rank, world, local_rank, clock_sampler):
                     "h2d_bytes_per_step": int(alg), "d2h_bytes_per_step": int(2 * n * 20),
                     "input": "Python lists of str -> validation_scores (UTF-32 encode, H2D, both kernels, D2H) -> all-reduce -> keep-mask all_gather"},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "edit_counts_kernel(chars)", "achieved": alg / chars_ms / 1e6, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "edit_bitpar_kernel(chars)", "achieved": alg / chars_ms / 1e6, "peak": peak,
                          "unit": "GB/s", "frac": alg / chars_ms / 1e6 / peak, "traffic": None, "peak_source": src,
                          "kernel_ms_per_launch": chars_ms, "GCUPS": cells / chars_ms / 1e6,
-                         "note": "integer-ALU / shared-memory bound (SURVEY 8d): GCUPS is the work rate, the HBM fraction is tiny by construction"},
+                         "note": "integer-ALU / latency bound (SURVEY 8d): GCUPS is the work rate, the HBM fraction is tiny by construction"},
             "quality": {"cer": cer_v, "wer": wer_v, "kept": kept, "kept_frac": kept / N},
             "parity_gate": {"per_pair_counts_bit_exact": True, "sample": int(len(sub))}, "cpu_baseline": cpu, "clocks": clocks,
         })

@@ -395,7 +395,9 @@ edit_bitpar_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
                    const int64_t* __restrict__ ref_end, const uint32_t* __restrict__ hyp_cps,
                    const int64_t* __restrict__ hyp_beg, const int64_t* __restrict__ hyp_end, int64_t n_pairs,
                    int mode, int32_t* __restrict__ out_sdih, int32_t* __restrict__ out_status,
-                   ulonglong2* __restrict__ area, int defer_status) {
+                   ulonglong2* __restrict__ area, int defer_status, int ppt) {
+  // ppt = pairs per tile (32, 16 or 8): a small batch is cut into more, smaller tiles so that every SM
+  // has warps to run -- a tile's phase A is serial over its pairs, which is the kernel's latency
   constexpr int WARPS = 4;
   using Sh = BitparShared<NW, WORDS>;
   constexpr int CAP = Sh::CAP, RAW = Sh::RAW, KR = RAW / 32;
@@ -412,10 +414,10 @@ edit_bitpar_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
   uint32_t* mask = sh.mask;
   for (int i = lane; i < kHashSlots; i += 32) { key[i] = kEmptyKey; mask[2 * i] = 0; mask[2 * i + 1] = 0; }
   __syncwarp();
-  const int64_t n_tiles = (n_pairs + 31) / 32;
+  const int64_t n_tiles = (n_pairs + ppt - 1) / ppt;
   for (int64_t tile = gw; tile < n_tiles; tile += nwarps) {
-    const int64_t base = tile * 32;
-    const int n_here = (int)min((int64_t)32, n_pairs - base);
+    const int64_t base = tile * ppt;
+    const int n_here = (int)min((int64_t)ppt, n_pairs - base);
     // this lane's pair
     int64_t my_r0 = 0, my_h0 = 0;
     int my_l1 = 0, my_l2 = 0;
@@ -731,7 +733,9 @@ static int32_t launch_bitpar(const uint32_t* ref_cps, const int64_t* ref_beg, co
                              int64_t n_pairs, int mode, int device, int32_t* out_sdih, int32_t* out_status,
                              int defer_status, cudaStream_t st) {
   const int sms = sm_count(device);
-  const int64_t tiles = (n_pairs + 31) / 32;
+  const int64_t warps = (int64_t)sms * MIN_CTAS * 4;  // resident at once
+  const int ppt = n_pairs >= 32 * warps ? 32 : (n_pairs >= 16 * warps ? 16 : 8);
+  const int64_t tiles = (n_pairs + ppt - 1) / ppt;
   const unsigned grid = (unsigned)std::min<int64_t>((tiles + 3) / 4, (int64_t)sms * MIN_CTAS);
   const size_t per_warp = (size_t)(64 * NW) * NW * 48 * sizeof(ulonglong2);  // VP / VN rows + pattern-match words
   uint8_t* area = nullptr;
@@ -739,7 +743,7 @@ static int32_t launch_bitpar(const uint32_t* ref_cps, const int64_t* ref_beg, co
   if (rc != CORAL_OK) return rc;
   edit_bitpar_kernel<NW, MIN_CTAS, WORDS><<<grid, 128, 0, st>>>(ref_cps, ref_beg, ref_end, hyp_cps, hyp_beg,
                                                                 hyp_end, n_pairs, mode, out_sdih, out_status,
-                                                                reinterpret_cast<ulonglong2*>(area), defer_status);
+                                                                reinterpret_cast<ulonglong2*>(area), defer_status, ppt);
   return CORAL_OK;
 }
 
