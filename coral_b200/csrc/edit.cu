@@ -197,6 +197,7 @@ edit_counts_kernel(const uint32_t* __restrict__ ref_cps, const int64_t* __restri
       }
     }
     if (n1 == 0) status = 1;
+    if (r1 < r0 || h1 < h0) { too_long = true; n1 = n2 = 0; }  // a span that ends before it begins: refused
     if (too_long) status = 2;
     __syncwarp();
     // remove_common_affix

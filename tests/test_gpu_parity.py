@@ -225,6 +225,13 @@ def test_edit_counts_capacity_is_reported_not_truncated(torch_cuda, rng):
     assert tuple(sdih.cpu().tolist()[1]) == oe.char_counts(refs[1], hyps[1])
     with pytest.raises(_lib.CoralError):
         metrics.edit_counts(["a" * 2100], ["b" * 2100], "chars")
+    # explicit spans: one that ends before it begins is refused (status 2), its neighbours are scored
+    beg = torch.tensor([0, 5, 9], dtype=torch.int64).cuda()
+    end = torch.tensor([4, 3, 12], dtype=torch.int64).cuda()
+    cps = d(encode_utf32(["kortkartabcx"])[0])
+    for mode, max_len in ((1, 16), (1, 600), (0, 16)):
+        sdih, status = metrics.edit_counts_spans_device(cps, beg, end, cps, beg, end, 3, mode, max_len)
+        assert status.cpu().tolist() == [0, 2, 0] and sdih.cpu().tolist() == [[0, 0, 0, 4], [0, 0, 0, 0], [0, 0, 0, 3]]
     # two streams, long strings (off-chip work areas), interleaved launches
     n = 64
     big_r = ["".join(rng.choice(list("abcdef "), size=int(rng.integers(200, 900)))) for _ in range(n)]
