@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import json
 import os
-import sys
 import time
 
 import numpy as np

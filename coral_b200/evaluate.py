@@ -16,7 +16,7 @@ import logging
 import numpy as np
 import pandas as pd
 
-from .metrics import _rate_from_counts, edit_counts
+from .metrics import _rate_from_counts
 
 logger = logging.getLogger(__name__)
 

@@ -15,7 +15,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .metrics import _rate_from_counts, edit_counts, per_sample_rates
+from .metrics import _rate_from_counts, per_sample_rates
 
 
 @dataclass
