@@ -455,9 +455,11 @@ class BeamSearchDecoderCTC:
         assembled on the GPU; the host decodes one flat UTF-32 buffer and slices it)."""
         return self._texts_from_device(*self.device_text(d_tok[:, None, :], d_lens[:, None]))
 
-    def _texts_from_device(self, d_cps, d_off, d_max) -> "DecodedTexts":
+    def _texts_from_device(self, d_cps, d_off, d_max, h_off=None, h_max=None) -> "DecodedTexts":
+        """Device text -> list of str. ``h_off`` / ``h_max``: the offsets and the longest length if they
+        have already been copied to the host (``_batch_launch`` queues those copies behind the kernels)."""
         B = d_off.numel() - 1
-        off = d_off.cpu()                                 # sync #1: offsets (and thereby the total)
+        off = d_off.cpu() if h_off is None else h_off     # sync #1: offsets (and thereby the total)
         o = off.tolist()
         total = o[-1]
         cps = d_cps[:total].cpu().numpy()                 # sync #2: exactly the code points
@@ -471,7 +473,7 @@ class BeamSearchDecoderCTC:
             flat = np.ascontiguousarray(cps.view(np.uint32))
             strings = _lib.load().coral_py_string_list(flat.ctypes.data, 4, off_np.ctypes.data, B)
         out = DecodedTexts(strings)
-        max_len = int(d_max.item()) if B else 0
+        max_len = (int(d_max.item()) if h_max is None else int(h_max)) if B else 0
         out._coral_dev = (d_cps[:total], d_off, max_len, ("decoded", next(DecodedTexts._tokens)))
         return out
 
@@ -614,24 +616,38 @@ class BeamSearchDecoderCTC:
             d_n, d_logit, d_comb, d_tok, d_lens, d_status, _ = self.decode_padded(
                 logits_list, lengths, beam_width, beam_prune_logp, token_min_logp, n_best=1, to_host=False)
             keep = (getattr(self, "_keepalive", None), logits_list, lengths)  # inputs outlive the launch
-        return (*self.device_text(d_tok, d_lens), d_status, keep)
+        d_cps, d_off, d_max = self.device_text(d_tok, d_lens)
+        # the small read-backs (capacity flag, longest transcript, offsets) are queued right behind the
+        # kernels, on the same stream, into pinned memory: collecting the batch later needs no kernel
+        # of its own -- which, behind a persistent decode of the NEXT batch, would wait for a free SM
+        B = d_off.numel() - 1
+        bad = d_status.abs().max().to(torch.int32).reshape(1) if d_status.numel() else \
+            torch.zeros(1, dtype=torch.int32, device=d_off.device)
+        h_small = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        h_small.copy_(torch.cat([bad, d_max.reshape(1).to(torch.int32)]), non_blocking=True)
+        h_off = torch.empty(B + 1, dtype=torch.int64, pin_memory=True)
+        h_off.copy_(d_off, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(d_off.device))
+        return (d_cps, d_off, d_max, d_status, keep, h_small, h_off, done)
 
     def _batch_finish(self, launched) -> "DecodedTexts":
-        d_cps, d_off, d_max, d_status, _keep = launched
-        # one small read-back tells whether any utterance ran out of arena capacity
-        bad_any = int(d_status.abs().max().item()) if d_status.numel() else 0
-        if bad_any:
+        d_cps, d_off, d_max, d_status, _keep, h_small, h_off, done = launched
+        done.synchronize()
+        if int(h_small[0]):  # some utterance ran out of arena capacity
             status = d_status.cpu().numpy()
             bad = np.nonzero(status)[0]
             raise _lib.CoralError(int(status[bad[0]]), f"decoder arena capacity exceeded for utterances {bad[:8].tolist()}")
-        return self._texts_from_device(d_cps, d_off, d_max)
+        return self._texts_from_device(d_cps, d_off, d_max, h_off, int(h_small[1]))
 
     def decode_batches(self, batches, beam_width: int = DEFAULT_BEAM_WIDTH,
                        beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
-                       prefetch: int = 1):
-        """(extension) ``decode_batch`` over an iterable of batches, one batch ahead: yields the
-        transcripts of batch k while batch k + 1 is already decoding, so the caller's host work on
-        batch k (strings, ``cer`` / ``wer``, bookkeeping) overlaps the next decode -- the loop
+                       prefetch: int = 2):
+        """(extension) ``decode_batch`` over an iterable of batches, ``prefetch`` batches ahead: yields
+        the transcripts of batch k while batch k + 1 is decoding and batch k + 2 is queued behind it, so
+        the caller's host work on batch k (strings, ``cer`` / ``wer``, bookkeeping) overlaps the next
+        decode and the GPU goes from one decode straight into the next (the small kernels the caller
+        queues for batch k run in the tail of decode k + 1) -- the loop
         ``for batch in dataloader: decode; score`` of R:src/coral/evaluate.py / validation.py.
 
         Every item of ``batches`` is either a list of ``[T_i, V]`` arrays or a ``(padded logits,
@@ -659,9 +675,7 @@ class BeamSearchDecoderCTC:
             pipe.wait_stream(torch.cuda.current_stream(dev))  # inputs produced on the caller's stream
             with torch.cuda.stream(pipe):
                 launched = self._batch_launch(logits, lengths, beam_width, beam_prune_logp, token_min_logp)
-                done = torch.cuda.Event()
-                done.record(pipe)
-            pending.append((launched, done))
+            pending.append(launched)
             return True
 
         more = True
@@ -671,12 +685,12 @@ class BeamSearchDecoderCTC:
                 more = launch()
             if not pending:
                 break
-            launched, done = pending.popleft()
+            launched = pending.popleft()
             if launched is None:
                 yield []
                 continue
             cur = torch.cuda.current_stream(dev)
-            cur.wait_event(done)
+            cur.wait_event(launched[-1])
             for t in launched[:4]:
                 t.record_stream(cur)  # allocated on the decoder's stream, consumed on the caller's
             yield self._batch_finish(launched)
