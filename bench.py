@@ -17,7 +17,7 @@ LM over a synthetic Danish-charset corpus. Weak scaling: every rank owns a full 
 `e2e`     the same metric through the public API with HOST inputs, every step: pinned logits
           pulled over PCIe by the decode -> transcripts to the host as Python strings ->
           cer()/wer() (references H2D, counts D2H). `e2e.value` drives the steps through
-          decoder.decode_batches (one batch ahead, as a dataset loop does);
+          decoder.decode_batches (two batches ahead, as a dataset loop does);
           `e2e.one_call_at_a_time` is decode_batch + cer/wer with nothing overlapped
 `roofline` for the beam-search kernel: algorithmic bytes / its CUDA-event time
 `cpu_baseline` the oracle (a port of pyctcdecode+KenLM+jiwer, which are not installable
