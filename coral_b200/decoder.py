@@ -680,20 +680,27 @@ class BeamSearchDecoderCTC:
 
         more = True
         depth = 1 + max(0, int(prefetch))
-        while True:
-            while more and len(pending) < depth:
-                more = launch()
-            if not pending:
-                break
-            launched = pending.popleft()
-            if launched is None:
-                yield []
-                continue
-            cur = torch.cuda.current_stream(dev)
-            cur.wait_event(launched[-1])
-            for t in launched[:4]:
-                t.record_stream(cur)  # allocated on the decoder's stream, consumed on the caller's
-            yield self._batch_finish(launched)
+        try:
+            while True:
+                while more and len(pending) < depth:
+                    more = launch()
+                if not pending:
+                    break
+                launched = pending.popleft()
+                if launched is None:
+                    yield []
+                    continue
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(launched[-1])
+                for t in launched[:4]:
+                    t.record_stream(cur)  # allocated on the decoder's stream, consumed on the caller's
+                yield self._batch_finish(launched)
+        finally:
+            # a caller that stops early (break, exception) leaves decodes in flight that read the
+            # caller's buffers in place: wait for them before those buffers can go away
+            if any(p is not None for p in pending):
+                pipe.synchronize()
+            pending.clear()
 
     # ------------------------------------------------------------- serialisation
     def save_to_dir(self, filepath: str) -> None:

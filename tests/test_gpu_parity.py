@@ -623,6 +623,11 @@ def test_decode_batches_one_ahead_equals_batch_by_batch(gpu_decoder, torch_cuda,
             assert metrics.cer(got, refs) == oe.cer(want[k], refs) and metrics.wer(got, refs) == oe.wer(want[k], refs)
             seen += 1
         assert seen == len(idxs)
+    # a caller that stops early: the decodes still in flight are waited for, later calls are unaffected
+    it = gpu_decoder.decode_batches(forms())
+    assert list(next(it)) == want[0]
+    it.close()
+    assert list(gpu_decoder.decode_batch(None, [w.logits[u, : w.lengths[u]] for u in idxs[2]])) == want[2]
     assert list(gpu_decoder.decode_batches([])) == []
     assert [list(x) for x in gpu_decoder.decode_batches([[], [w.logits[3, : w.lengths[3]]]])] == \
         [[], list(gpu_decoder.decode_batch(None, [w.logits[3, : w.lengths[3]]]))]
