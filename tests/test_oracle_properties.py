@@ -151,3 +151,77 @@ def test_eos_scores_empty_last_word_as_unk(tmp_path):
     ph, sth = m.base_score(st0, "hej")
     pe2, _ = m.base_score(sth, "</s>")
     assert abs((a[4] - a[3]) - (0.5 * (ph + pe2) * LOG_BASE_CHANGE_FACTOR + 1.5)) < 1e-9
+
+
+def test_bit_parallel_recurrence_gives_the_same_edit_script_counts():
+    """The algorithm of the GPU's bit-parallel edit kernel (Hyyro's recurrence in 64-bit words with
+    carries between the words, VP / VN recorded per row, recover_alignment's walk over them, substitutions
+    = distance - deletions - insertions), restated here in Python integers, gives the oracle's (S, D, I)
+    on the cores that are left after remove_common_affix -- including patterns of 63 / 64 / 65 / 128 / 129
+    / 200 symbols (one, two, three and four words)."""
+    import random
+
+    from oracle.edit import editops_counts, remove_common_affix
+
+    M64 = (1 << 64) - 1
+
+    def bitpar(a, b):
+        m1, m2 = len(a), len(b)
+        if m1 == 0 or m2 == 0:
+            return 0, m1, m2
+        nw = (m1 + 63) // 64
+        pm = [{} for _ in range(nw)]
+        for i, c in enumerate(a):
+            pm[i >> 6][c] = pm[i >> 6].get(c, 0) | (1 << (i & 63))
+        vp, vn, dist, rows = [M64] * nw, [0] * nw, m1, []
+        last = 1 << ((m1 - 1) & 63)
+        for ch in b:
+            hp_c, hn_c, row = 1, 0, []
+            for w in range(nw):
+                x = pm[w].get(ch, 0) | hn_c
+                d0 = ((((x & vp[w]) + vp[w]) & M64) ^ vp[w]) | x | vn[w]
+                hp = vn[w] | (~(d0 | vp[w]) & M64)
+                hn = d0 & vp[w]
+                if w == nw - 1:
+                    dist += ((hp & last) != 0) - ((hn & last) != 0)
+                hps, hns = ((hp << 1) & M64) | hp_c, ((hn << 1) & M64) | hn_c
+                hp_c, hn_c = hp >> 63, hn >> 63
+                vp[w] = hns | (~(d0 | hps) & M64)
+                vn[w] = hps & d0
+                row.append((vp[w], vn[w]))
+            rows.append(row)
+        col, r, dele, ins = m1, m2, 0, 0
+        while r and col:
+            w, bit = (col - 1) >> 6, (col - 1) & 63
+            if (rows[r - 1][w][0] >> bit) & 1:
+                dele += 1
+                col -= 1
+            else:
+                r -= 1
+                if r and (rows[r - 1][w][1] >> bit) & 1:
+                    ins += 1
+                else:
+                    col -= 1
+        dele += col
+        ins += r
+        return dist - dele - ins, dele, ins
+
+    rnd = random.Random(11)
+    for t in range(1200):
+        alpha = "ab" if t % 3 == 0 else "abcdefgh"
+        n1 = rnd.choice([1, 2, 5, 30, 63, 64, 65, 100, 128, 129, 200])
+        a = [rnd.choice(alpha) for _ in range(n1)]
+        if t % 2:
+            b = list(a)
+            for _ in range(rnd.randint(0, 12)):
+                k, x = rnd.randrange(len(b) + 1), rnd.random()
+                if x < 0.3 and b:
+                    b.pop(min(k, len(b) - 1))
+                elif x < 0.6:
+                    b.insert(k, rnd.choice(alpha))
+                elif b:
+                    b[min(k, len(b) - 1)] = rnd.choice(alpha)
+        else:
+            b = [rnd.choice(alpha) for _ in range(rnd.choice([1, 3, 20, 64, 70, 130, 250]))]
+        ca, cb = remove_common_affix(a, b)
+        assert bitpar(ca, cb) == tuple(editops_counts(a, b)), (t, n1, len(b))
