@@ -24,7 +24,7 @@ import re
 import numpy as np
 
 from . import _lib
-from .textio import decode_utf32, encode_utf32
+from .textio import encode_utf32
 
 # R:src/coral/data.py:47-90 -- the characters to convert, applied in this order
 DEFAULT_CONVERSION_DICT = {
@@ -78,8 +78,8 @@ class TextNormaliser:
         total = C.c_int64()
         _lib.check(lib.coral_normaliser_run(self._h, cps.ctypes.data, off.ctypes.data, len(texts),
                                             n_threads or _threads(), C.byref(total)))
-        out_cps = np.zeros(max(total.value, 1), dtype=np.uint32)
-        out_off = np.zeros(len(texts) + 1, dtype=np.int64)
+        out_cps = np.empty(max(total.value, 1), dtype=np.uint32)
+        out_off = np.empty(len(texts) + 1, dtype=np.int64)
         status = np.zeros(len(texts), dtype=np.int32)
         _lib.check(lib.coral_normaliser_fetch(self._h, out_cps.ctypes.data, out_off.ctypes.data, status.ctypes.data))
         if status.any():
@@ -87,7 +87,8 @@ class TextNormaliser:
             raise NotImplementedError(
                 f"text {i} ({texts[i]!r}) holds a Greek capital sigma (lower_case) or a non-ASCII decimal digit "
                 "(convert_numerals): not restated by coral_b200's normaliser")
-        return decode_utf32(out_cps[: total.value], out_off)
+        # one C loop builds the list of str from the flat buffer (as decode_batch does)
+        return lib.coral_py_string_list(out_cps.ctypes.data, 4, out_off.ctypes.data, len(texts))
 
     def __del__(self):
         try:
